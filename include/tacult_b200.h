@@ -1,0 +1,205 @@
+/*
+ * tacult_b200 — C ABI of the B200-native self-play hot path.
+ *
+ * The reference (lunathanael/tacult) has no FFI of its own: its hot path is three
+ * duck-typed Python protocols.  Each entry point below names the
+ * reference interface it stands in for; tacult_b200/*.py binds them with ctypes and
+ * re-creates those Python protocols on top (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns TC_OK (0) or a negative TC_E* code; tc_last_error()
+ *     returns a human-readable message for the calling thread's last failure;
+ *   - pointers named *_host are host buffers owned by the caller, *_dev are device
+ *     pointers on the engine's device; no torch types cross this boundary;
+ *   - an engine handle is not thread-safe; all work is issued on the engine's CUDA
+ *     stream (tc_set_stream) and the host-buffer calls synchronise before returning.
+ *
+ * Position format ("canonical frame", what VectorizedMCTS and the network always see:
+ * side to move == 1 and its stones in `board`, /root/reference/src/tacult/utac_game.py:83-107)
+ *   fields form : uint16 board[9], uint16 occ[9], int8 last_square   — GAMESTATE members,
+ *                 bit k of sub-board i is global cell (3*(i/3)+k/3, 3*(i%3)+k%3)
+ *                 (utac_game.py:259-265,283-291)
+ *   packed form : 8 x uint32: w[g] (g=0..2) = board[3g] | board[3g+1]<<9 | board[3g+2]<<18,
+ *                 w[3+g] = the same for occ, w[6] bits 0..3 = last_square+1, w[7] = 0.
+ */
+#ifndef TACULT_B200_H
+#define TACULT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TC_ABI_VERSION 1
+#define TC_ACTIONS 81
+#define TC_STATE_WORDS 8
+
+enum {
+    TC_OK = 0,
+    TC_EINVAL = -1,     /* bad argument */
+    TC_ECUDA = -2,      /* CUDA runtime / driver failure */
+    TC_ECAPACITY = -3,  /* a tree ran out of node / edge / hash capacity */
+    TC_ESTATE = -4,     /* call sequence error (e.g. search before weights are loaded) */
+    TC_EILLEGAL = -5    /* an illegal move was requested */
+};
+
+enum {
+    TC_EVAL_NET_F32 = 0,   /* fp32 CUDA-core forward: parity mode, 1e-3 of the reference net */
+    TC_EVAL_NET_BF16 = 1,  /* bf16 tcgen05/TMEM trunk: production mode, 2e-2 */
+    TC_EVAL_HASH = 2       /* deterministic integer-hash priors/values: bit-exact visit-count tests */
+};
+
+/* terminal status of a canonical position, seen by its side to move */
+enum { TC_LIVE = 0, TC_LOST = 1, TC_DRAW = 2, TC_WON = 3 };
+
+typedef struct tc_engine tc_engine;
+
+typedef struct {
+    int32_t num_envs;            /* trees searched in lock-step == args.numEnvs (mcts.py:152-162) */
+    int32_t max_nodes_per_tree;  /* node pool per tree; the reference never prunes inside a game */
+    int32_t max_edges_per_tree;  /* legal-move edge pool per tree; 0 = 12 x max_nodes_per_tree */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t evaluator;           /* TC_EVAL_* */
+    int32_t eval_log_capacity;   /* >0: keep the first N leaf evaluations (state, pi, v) for replay tests */
+    uint64_t hash_salt;          /* TC_EVAL_HASH parameters (oracle/evaluators.py) */
+    int32_t hash_pi_levels;
+    int32_t hash_v_levels;
+} tc_config;
+
+/* shape of `_UtacNNet` (/root/reference/src/tacult/network.py:44-79) */
+typedef struct {
+    int32_t channels;
+    int32_t num_residual_blocks;
+    int32_t embedding_size;
+    int32_t in_planes;           /* 4 in the reference (network.py:55) */
+} tc_net_desc;
+
+/* counters SURVEY.md §8(d) asks the kernels to export (summed over trees since the last reset) */
+typedef struct {
+    uint64_t sims;               /* simulations started from a live root */
+    uint64_t sum_depth;          /* interior levels traversed (PUCT selections) */
+    uint64_t sum_legal;          /* legal edges scanned by those selections */
+    uint64_t nn_leaves;          /* leaves sent to the evaluator */
+    uint64_t sum_leaf_legal;     /* legal moves of those leaves (edges written at expansion) */
+    uint64_t terminal_leaves;    /* simulations that ended in a finished game */
+    uint64_t transpositions;     /* first visits of an edge whose successor already existed */
+    uint64_t nodes_in_use;       /* node pool entries in use, all trees */
+    uint64_t edges_in_use;
+    uint64_t max_nodes_one_tree;
+    uint64_t max_edges_one_tree;
+    uint64_t kernel_launches;    /* kernels this library launched since the last tc_reset_stats */
+} tc_stats;
+
+int         tc_abi_version(void);
+const char *tc_last_error(void);
+
+/* ---- rules engine hooks: replace utac_gym.core.GameState methods (external C++ `utac`;
+ *      call sites /root/reference/src/tacult/utac_game.py:45-46,62,75-81,248) -------------- */
+/* make_move + getCanonicalForm: out[i] = canonical successor of states[i] after actions[i];
+ * status[i] = TC_* of the successor (utac_game.py:34-47,64-107).  Illegal action -> TC_EILLEGAL. */
+int tc_rules_step(int n, const uint32_t *states_host, const int8_t *actions_host,
+                  uint32_t *out_states_host, int8_t *status_host);
+/* get_valid_mask (utac_game.py:62): mask[i][a] in {0,1}, action order */
+int tc_rules_legal_mask(int n, const uint32_t *states_host, uint8_t *mask_host);
+/* is_terminal/terminal_value (utac_game.py:64-81) */
+int tc_rules_status(int n, const uint32_t *states_host, int8_t *status_host);
+/* get_obs (utac_game.py:247-250, base/utils.py:7-10): obs[i][4][9][9] float32 */
+int tc_rules_encode_obs(int n, const uint32_t *states_host, float *obs_host);
+/* seeded random playouts on the device, spec shared with oracle/utac_rules.c:utac_playout */
+typedef struct {
+    uint64_t checksum;
+    uint32_t final_state[TC_STATE_WORDS];
+    int32_t plies;
+    int32_t outcome;
+} tc_playout_result;
+int tc_rules_playouts(uint64_t seed, uint64_t first_game, int n, int max_plies, tc_playout_result *out_host);
+
+/* ---- search engine: replaces VectorizedMCTS (/root/reference/src/tacult/base/mcts.py:147-358) ---- */
+int tc_create(const tc_config *cfg, tc_engine **out);              /* VectorizedMCTS.__init__ mcts.py:152-162 */
+int tc_destroy(tc_engine *e);
+int tc_set_stream(tc_engine *e, void *cuda_stream);                /* cudaStream_t; NULL = engine-owned stream */
+int tc_reset(tc_engine *e, int env);                               /* VectorizedMCTS.reset(i) mcts.py:165-172; env<0 = all */
+int tc_set_hash_evaluator(tc_engine *e, uint64_t salt, int pi_levels, int v_levels);
+int tc_set_evaluator(tc_engine *e, int evaluator);
+/* roots for the next tc_search: canonicalBoards of getActionProbs (mcts.py:175).  active[i]==0 marks a
+ * None board (mcts.py:235-239).  Terminal boards are accepted and simply do nothing (mcts.py:250-258). */
+int tc_set_roots(tc_engine *e, const uint16_t *board_host, const uint16_t *occ_host,
+                 const int8_t *last_square_host, const uint8_t *active_host);
+int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, const uint8_t *active_host);
+/* num_sims x VectorizedMCTS.search (mcts.py:184-185,217-342); cpuct read per call like args.cpuct (mcts.py:309) */
+int tc_search(tc_engine *e, int num_sims, double cpuct);
+/* root edge visit counts, the `_counts` of getActionProbs (mcts.py:191-198): counts[i][a] */
+int tc_root_counts(tc_engine *e, uint32_t *counts_host);
+/* root edge mean values Q (mcts.py:156), NaN where the edge was never visited; test hook */
+int tc_root_q(tc_engine *e, double *q_host);
+int tc_get_stats(tc_engine *e, tc_stats *out);
+int tc_reset_stats(tc_engine *e);
+/* leaf evaluations recorded when cfg.eval_log_capacity > 0: returns how many, copies up to `max` */
+int tc_eval_log(tc_engine *e, int max, uint32_t *states_host, float *pi_host, float *v_host, int *count_out);
+
+/* ---- evaluator: replaces NNetWrapper.predict + _UtacNNet.forward
+ *      (/root/reference/src/tacult/base/nn_wrapper.py:125-136, network.py:81-102) ------------------------ */
+/* blob = the reference state_dict tensors, float32, concatenated in this order:
+ *   conv_in.{weight,bias}, bn_in.{weight,bias,running_mean,running_var},
+ *   for k in blocks: resnet.k.conv_block1.0.{weight,bias}, resnet.k.conv_block1.1.{weight,bias,running_mean,running_var},
+ *                    resnet.k.conv_block2.0.{...}, resnet.k.conv_block2.1.{...},
+ *   fc1.{weight,bias}, fc_bn1.{weight,bias,running_mean,running_var}, pi.{weight,bias}, v.{weight,bias}
+ * BatchNorm (eps 1e-5) is folded into the preceding layer inside the library. */
+int tc_load_weights(tc_engine *e, const tc_net_desc *desc, const float *blob_host, size_t n_floats);
+size_t tc_weight_blob_floats(const tc_net_desc *desc);
+/* predict: obs[B][in_planes][9][9] f32 -> pi[B][81] (unmasked softmax, network.py:99), v[B] (tanh).
+ * `evaluator` selects TC_EVAL_NET_F32 or TC_EVAL_NET_BF16.  logits_host may be NULL. */
+int tc_forward(tc_engine *e, int evaluator, int batch, const float *obs_host, float *pi_host, float *v_host,
+               float *logits_host);
+/* the same from packed positions (observation planes built on the device) */
+int tc_forward_states(tc_engine *e, int evaluator, int batch, const uint32_t *states_host, float *pi_host,
+                      float *v_host);
+/* device-resident variant used for throughput sweeps: obs already in HBM as packed states */
+int tc_forward_states_dev(tc_engine *e, int evaluator, int batch, const uint32_t *states_dev, float *pi_dev,
+                          float *v_dev);
+
+/* ---- device-resident self-play driver: Coach.executeEpisode semantics
+ *      (/root/reference/src/tacult/base/coach.py:87-157) without host round trips ------------------------- */
+typedef struct {
+    int32_t num_sims;            /* args.numMCTSSims */
+    int32_t temp_threshold;      /* args.tempThreshold: tau=1 while episodeStep < threshold (coach.py:124-125) */
+    int32_t auto_reset;          /* 1: a finished env restarts a new game with a fresh tree (the reference's
+                                    commented-out block coach.py:114-122); 0: it idles like the reference */
+    int32_t reserved;
+    double cpuct;
+    uint64_t seed;
+} tc_selfplay_config;
+typedef struct {
+    uint64_t plies;              /* env-plies played (live envs only) */
+    uint64_t sims;               /* live envs x num_sims summed over plies == the BASELINE.json metric numerator */
+    uint64_t games_finished;
+    uint64_t first_player_wins, second_player_wins, draws;
+    uint64_t examples;           /* trajectory records available */
+} tc_selfplay_stats;
+/* one record per env-ply: what coach.py:136-138 stores before symmetry augmentation */
+typedef struct {
+    uint32_t state[TC_STATE_WORDS];   /* canonical position */
+    uint16_t counts[TC_ACTIONS];      /* root visit counts (pi = counts/sum or one-hot, per tau) */
+    int8_t action;                    /* move played */
+    int8_t tau_one;                   /* 1 if sampled with tau=1 */
+    int8_t player;                    /* +1 first player, -1 second */
+    int8_t z_sign;                    /* filled at game end: +1 win, -1 loss, 0 draw for `player` (coach.py:149) */
+    int32_t env;
+    int32_t game;                     /* per-env game ordinal */
+    int32_t ply;
+    int32_t finished;                 /* 1 once z_sign is final */
+} tc_example;
+int tc_selfplay_begin(tc_engine *e, const tc_selfplay_config *cfg);
+int tc_selfplay_step(tc_engine *e, int plies);      /* plays `plies` lock-step plies; asynchronous on the stream */
+int tc_selfplay_sync(tc_engine *e);
+int tc_selfplay_get_stats(tc_engine *e, tc_selfplay_stats *out);
+/* copies finished-game records to the host (or leaves them on the device for NCCL): returns count */
+int tc_selfplay_drain(tc_engine *e, int max, tc_example *out_host, int *count_out);
+int tc_selfplay_drain_dev(tc_engine *e, int max, tc_example *out_dev, int *count_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACULT_B200_H */
