@@ -3,7 +3,7 @@
  *
  * The reference (lunathanael/tacult) has no FFI of its own: its hot path is three
  * duck-typed Python protocols.  Each entry point below names the
- * reference interface it stands in for; tacult_b200/*.py binds them with ctypes and
+ * reference interface it stands in for; the Python modules under tacult_b200/ bind them with ctypes and
  * re-creates those Python protocols on top (INTEGRATION.md shows the stub).
  *
  * Conventions
@@ -185,11 +185,11 @@ typedef struct {
     int8_t action;                    /* move played */
     int8_t tau_one;                   /* 1 if sampled with tau=1 */
     int8_t player;                    /* +1 first player, -1 second */
-    int8_t z_sign;                    /* filled at game end: +1 win, -1 loss, 0 draw for `player` (coach.py:149) */
+    int8_t z_sign;                    /* filled at game end: sign of z for `player`, coach.py:143-149 */
     int32_t env;
     int32_t game;                     /* per-env game ordinal */
     int32_t ply;
-    int32_t finished;                 /* 1 once z_sign is final */
+    int32_t finished;                 /* 0 game in progress; 1 decisive: z = z_sign; 2 draw: z = z_sign * 1e-4 */
 } tc_example;
 int tc_selfplay_begin(tc_engine *e, const tc_selfplay_config *cfg);
 int tc_selfplay_step(tc_engine *e, int plies);      /* plays `plies` lock-step plies; asynchronous on the stream */

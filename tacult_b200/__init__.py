@@ -1,0 +1,11 @@
+"""tacult_b200 — B200-native engine for tacult's self-play hot path (vectorised MCTS + UTTT rules +
+dual-head ResNet forward).  Host side mirrors the reference's Python protocols; the work is CUDA
+(sm_100a) behind the C ABI in include/tacult_b200.h.  No CPU fallback exists."""
+from . import _lib
+from .engine import (Engine, pack_fields, pack_gamestates, rules_encode_obs, rules_legal_mask, rules_playouts,
+                     rules_status, rules_step)
+from .evaluator import B200Evaluator
+from .mcts import VectorizedMCTS
+
+__all__ = ["Engine", "VectorizedMCTS", "B200Evaluator", "pack_fields", "pack_gamestates", "rules_step",
+           "rules_legal_mask", "rules_status", "rules_encode_obs", "rules_playouts", "_lib"]

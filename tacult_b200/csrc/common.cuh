@@ -1,0 +1,72 @@
+// Shared host/device helpers for the tacult_b200 CUDA library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/tacult_b200.h"
+
+namespace tc {
+
+void set_error(const char *fmt, ...);
+
+#define TC_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            tc::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return TC_ECUDA;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+#define TC_CHECK(cond, code, ...)                                                                  \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            tc::set_error(__VA_ARGS__);                                                            \
+            return (code);                                                                         \
+        }                                                                                          \
+    } while (0)
+
+#define TC_TRY(expr)                                                                               \
+    do {                                                                                           \
+        int _r = (expr);                                                                           \
+        if (_r != TC_OK) return _r;                                                                \
+    } while (0)
+
+constexpr int SM_COUNT = 148;      // B200: 2 dies x 74 SMs
+constexpr int WARP = 32;
+
+template <typename T>
+struct DevBuf {                     // RAII device allocation
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept
+    {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace tc

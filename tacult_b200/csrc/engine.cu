@@ -1,0 +1,643 @@
+// C ABI of the search engine and evaluator (include/tacult_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "nn.cuh"
+#include "nn_bf16.cuh"
+#include "selfplay.cuh"
+#include "tree.cuh"
+
+namespace tc {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+__global__ void k_log_append(TreeStore ts, uint32_t *log_states, float *log_pi, float *log_v, int *log_count,
+                             int capacity)
+{
+    const int rows = *ts.eval_count;
+    const int base = *log_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * 81; i += gridDim.x * blockDim.x) {
+        int row = i / 81, a = i % 81;
+        if (base + row >= capacity) continue;
+        log_pi[(size_t)(base + row) * 81 + a] = ts.eval_pi[(size_t)row * 81 + a];
+        if (a < 8) log_states[(size_t)(base + row) * 8 + a] = ts.eval_state[(size_t)row * 8 + a];
+        if (a == 8) log_v[base + row] = ts.eval_v[row];
+    }
+}
+
+__global__ void k_log_advance(TreeStore ts, int *log_count) { *log_count += *ts.eval_count; }
+
+__global__ void k_tree_totals(TreeStore ts, unsigned long long *out)
+{
+    // out[0..6] counters, [7] nodes, [8] edges, [9] max nodes, [10] max edges
+    unsigned long long acc[11];
+    for (int k = 0; k < 11; ++k) acc[k] = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ts.E; t += gridDim.x * blockDim.x) {
+        const TreeCtl &c = ts.ctl[t];
+        acc[0] += c.sims; acc[1] += c.sum_depth; acc[2] += c.sum_legal; acc[3] += c.nn_leaves;
+        acc[4] += c.sum_leaf_legal; acc[5] += c.terminal_leaves; acc[6] += c.transpositions;
+        acc[7] += c.n_nodes; acc[8] += c.n_edges;
+        acc[9] = max(acc[9], (unsigned long long)c.n_nodes);
+        acc[10] = max(acc[10], (unsigned long long)c.n_edges);
+    }
+    for (int k = 0; k < 9; ++k) atomicAdd(out + k, acc[k]);
+    atomicMax(out + 9, acc[9]);
+    atomicMax(out + 10, acc[10]);
+}
+
+__global__ void k_zero_counters(TreeStore ts)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ts.E) return;
+    TreeCtl &c = ts.ctl[t];
+    c.sims = c.sum_depth = c.sum_legal = c.nn_leaves = c.sum_leaf_legal = c.terminal_leaves = c.transpositions = 0;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+struct tc_engine {
+    tc_config cfg{};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    TreeStore ts{};
+    DevBuf<uint4> node_hdr, path;
+    DevBuf<uint32_t> node_Ns, hash, eval_state, root_states, counts;
+    DevBuf<unsigned long long> edge_mem, totals;
+    DevBuf<TreeCtl> ctl;
+    DevBuf<float> eval_pi, eval_v;
+    DevBuf<int> eval_count, error_flag, log_count;
+    DevBuf<uint8_t> root_active;
+    DevBuf<uint16_t> fld_board, fld_occ;
+    DevBuf<int8_t> fld_last;
+    DevBuf<double> root_q;
+    // evaluation log
+    DevBuf<uint32_t> log_states;
+    DevBuf<float> log_pi, log_v;
+    // evaluator
+    int evaluator = TC_EVAL_HASH;
+    HashEvalParams hash_params{};
+    FoldedNet folded;
+    NetF32 net32;
+    NetBF16 net16;
+    bool have_weights = false;
+    // scratch for tc_forward
+    DevBuf<float> fwd_obs, fwd_pi, fwd_v, fwd_logits;
+    DevBuf<uint32_t> fwd_states;
+    int fwd_capacity = 0;
+    // self-play
+    SelfPlayStore sp{};
+    tc_selfplay_config sp_cfg{};
+    bool sp_ready = false;
+    DevBuf<EnvState> sp_env;
+    DevBuf<tc_example> sp_pending, sp_finished;
+    DevBuf<int> sp_finished_count;
+    DevBuf<unsigned long long> sp_stats;
+    unsigned long long launches = 0;
+};
+
+static int check_engine(tc_engine *e)
+{
+    TC_CHECK(e != nullptr, TC_EINVAL, "null engine handle");
+    TC_CUDA(cudaSetDevice(e->cfg.device));
+    return TC_OK;
+}
+
+static int check_device_errors(tc_engine *e)
+{
+    int flag = 0;
+    TC_CUDA(cudaMemcpyAsync(&flag, e->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    if (flag != 0) {
+        cudaMemsetAsync(e->error_flag.p, 0, sizeof(int), e->stream);
+        TC_CHECK(flag != 1, TC_ECAPACITY,
+                 "a tree exhausted its node/edge/hash pool (max_nodes_per_tree=%d, max_edges_per_tree=%u); "
+                 "raise the capacities in tc_config", e->cfg.max_nodes_per_tree, e->ts.capE);
+        TC_CHECK(false, TC_ESTATE, "search kernel found a live position without legal moves (flag %d)", flag);
+    }
+    return TC_OK;
+}
+
+extern "C" int tc_abi_version(void) { return TC_ABI_VERSION; }
+extern "C" const char *tc_last_error(void) { return g_error; }
+
+extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
+{
+    TC_CHECK(cfg && out, TC_EINVAL, "tc_create: null argument");
+    TC_CHECK(cfg->num_envs >= 1, TC_EINVAL, "num_envs must be >= 1");
+    TC_CHECK(cfg->max_nodes_per_tree >= 2 && (uint32_t)cfg->max_nodes_per_tree <= MAX_NODES_PER_TREE, TC_EINVAL,
+             "max_nodes_per_tree out of range [2, %u]", MAX_NODES_PER_TREE);
+    TC_CHECK(cfg->evaluator >= TC_EVAL_NET_F32 && cfg->evaluator <= TC_EVAL_HASH, TC_EINVAL, "unknown evaluator %d",
+             cfg->evaluator);
+    int ndev = 0;
+    TC_CUDA(cudaGetDeviceCount(&ndev));
+    TC_CHECK(cfg->device >= 0 && cfg->device < ndev, TC_EINVAL, "device %d not present (%d visible)", cfg->device, ndev);
+    TC_CUDA(cudaSetDevice(cfg->device));
+    tc_engine *e = new tc_engine();
+    e->cfg = *cfg;
+    e->evaluator = cfg->evaluator;
+    e->hash_params.salt = cfg->hash_salt;
+    e->hash_params.pi_levels = cfg->hash_pi_levels;
+    e->hash_params.v_levels = cfg->hash_v_levels;
+    const size_t E = cfg->num_envs, capN = cfg->max_nodes_per_tree;
+    const size_t capE = cfg->max_edges_per_tree > 0 ? (size_t)cfg->max_edges_per_tree : 12 * capN;
+    size_t hs = 64;
+    while (hs < 2 * capN) hs <<= 1;
+    auto fail = [&](int code) {
+        delete e;
+        return code;
+    };
+#define TC_ALLOC(buf, count)                                                                           \
+    do {                                                                                               \
+        cudaError_t _e = (buf).alloc(count);                                                           \
+        if (_e != cudaSuccess) {                                                                       \
+            set_error("tc_create: cudaMalloc of %zu bytes failed: %s", (size_t)(buf).bytes(),          \
+                      cudaGetErrorString(_e));                                                         \
+            return fail(TC_ECUDA);                                                                     \
+        }                                                                                              \
+    } while (0)
+    TC_ALLOC(e->node_hdr, 2 * E * capN);
+    TC_ALLOC(e->node_Ns, E * capN);
+    TC_ALLOC(e->edge_mem, 3 * E * capE);
+    TC_ALLOC(e->hash, E * hs);
+    TC_ALLOC(e->ctl, E);
+    TC_ALLOC(e->path, E * MAX_DEPTH);
+    TC_ALLOC(e->eval_state, 8 * E);
+    TC_ALLOC(e->eval_pi, 81 * E);
+    TC_ALLOC(e->eval_v, E);
+    TC_ALLOC(e->eval_count, 1);
+    TC_ALLOC(e->error_flag, 1);
+    TC_ALLOC(e->root_states, 8 * E);
+    TC_ALLOC(e->root_active, E);
+    TC_ALLOC(e->counts, 81 * E);
+    TC_ALLOC(e->root_q, 81 * E);
+    TC_ALLOC(e->fld_board, 9 * E);
+    TC_ALLOC(e->fld_occ, 9 * E);
+    TC_ALLOC(e->fld_last, E);
+    TC_ALLOC(e->totals, 16);
+    TC_ALLOC(e->log_count, 1);
+    if (cfg->eval_log_capacity > 0) {
+        TC_ALLOC(e->log_states, 8 * (size_t)cfg->eval_log_capacity);
+        TC_ALLOC(e->log_pi, 81 * (size_t)cfg->eval_log_capacity);
+        TC_ALLOC(e->log_v, (size_t)cfg->eval_log_capacity);
+    }
+#undef TC_ALLOC
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("tc_create: cudaStreamCreate failed");
+        return fail(TC_ECUDA);
+    }
+    e->stream = e->own_stream;
+    TreeStore &ts = e->ts;
+    ts.E = (int)E;
+    ts.capN = (uint32_t)capN;
+    ts.capE = (uint32_t)capE;
+    ts.hashSize = (uint32_t)hs;
+    ts.node_hdr = e->node_hdr.p;
+    ts.node_Ns = e->node_Ns.p;
+    ts.edge_mem = e->edge_mem.p;
+    ts.hash = e->hash.p;
+    ts.ctl = e->ctl.p;
+    ts.path = e->path.p;
+    ts.eval_state = e->eval_state.p;
+    ts.eval_pi = e->eval_pi.p;
+    ts.eval_v = e->eval_v.p;
+    ts.eval_count = e->eval_count.p;
+    ts.error_flag = e->error_flag.p;
+    cudaMemsetAsync(e->ctl.p, 0, e->ctl.bytes(), e->stream);
+    cudaMemsetAsync(e->error_flag.p, 0, sizeof(int), e->stream);
+    cudaMemsetAsync(e->eval_count.p, 0, sizeof(int), e->stream);
+    cudaMemsetAsync(e->log_count.p, 0, sizeof(int), e->stream);
+    cudaMemsetAsync(e->root_active.p, 0, e->root_active.bytes(), e->stream);
+    launch_reset(ts, -1, e->stream);
+    e->launches += 1;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        set_error("tc_create: device initialisation failed");
+        return fail(TC_ECUDA);
+    }
+    *out = e;
+    return TC_OK;
+}
+
+extern "C" int tc_destroy(tc_engine *e)
+{
+    if (!e) return TC_OK;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return TC_OK;
+}
+
+extern "C" int tc_set_stream(tc_engine *e, void *cuda_stream)
+{
+    TC_TRY(check_engine(e));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return TC_OK;
+}
+
+extern "C" int tc_reset(tc_engine *e, int env)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(env < e->ts.E, TC_EINVAL, "tc_reset: env %d out of range", env);
+    launch_reset(e->ts, env, e->stream);
+    e->launches += 1;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+extern "C" int tc_set_hash_evaluator(tc_engine *e, uint64_t salt, int pi_levels, int v_levels)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(pi_levels >= 0 && v_levels >= 0 && v_levels <= 4, TC_EINVAL, "bad hash evaluator levels");
+    e->hash_params.salt = salt;
+    e->hash_params.pi_levels = pi_levels;
+    e->hash_params.v_levels = v_levels;
+    return TC_OK;
+}
+
+extern "C" int tc_set_evaluator(tc_engine *e, int evaluator)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(evaluator >= TC_EVAL_NET_F32 && evaluator <= TC_EVAL_HASH, TC_EINVAL, "unknown evaluator %d", evaluator);
+    e->evaluator = evaluator;
+    return TC_OK;
+}
+
+static int set_roots_dev(tc_engine *e, const uint8_t *active_host)
+{
+    if (active_host)
+        TC_CUDA(cudaMemcpyAsync(e->root_active.p, active_host, e->ts.E, cudaMemcpyHostToDevice, e->stream));
+    launch_set_roots(e->ts, e->root_states.p, active_host ? e->root_active.p : nullptr, e->stream);
+    e->launches += 1;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(e->stream));     // the host buffers may be reused by the caller
+    return TC_OK;
+}
+
+extern "C" int tc_set_roots(tc_engine *e, const uint16_t *board_host, const uint16_t *occ_host,
+                            const int8_t *last_square_host, const uint8_t *active_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(board_host && occ_host && last_square_host, TC_EINVAL, "tc_set_roots: null buffer");
+    const int E = e->ts.E;
+    TC_CUDA(cudaMemcpyAsync(e->fld_board.p, board_host, 9 * (size_t)E * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                            e->stream));
+    TC_CUDA(cudaMemcpyAsync(e->fld_occ.p, occ_host, 9 * (size_t)E * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                            e->stream));
+    TC_CUDA(cudaMemcpyAsync(e->fld_last.p, last_square_host, (size_t)E, cudaMemcpyHostToDevice, e->stream));
+    launch_pack_fields(E, e->fld_board.p, e->fld_occ.p, e->fld_last.p, e->root_states.p, e->stream);
+    e->launches += 1;
+    return set_roots_dev(e, active_host);
+}
+
+extern "C" int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, const uint8_t *active_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(states_host, TC_EINVAL, "tc_set_roots_packed: null buffer");
+    TC_CUDA(cudaMemcpyAsync(e->root_states.p, states_host, 8 * (size_t)e->ts.E * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, e->stream));
+    return set_roots_dev(e, active_host);
+}
+
+// one lock-step simulation for every tree: select -> evaluate leaves -> expand + backup
+static int enqueue_simulation(tc_engine *e, double cpuct)
+{
+    TC_CUDA(cudaMemsetAsync(e->eval_count.p, 0, sizeof(int), e->stream));
+    launch_select(e->ts, cpuct, e->stream);
+    e->launches += 1;
+    if (e->evaluator == TC_EVAL_HASH) {
+        launch_hash_eval(e->ts, e->hash_params, e->stream);
+        e->launches += 1;
+    } else if (e->evaluator == TC_EVAL_NET_F32) {
+        e->launches += e->net32.forward(e->ts.E, e->eval_count.p, e->eval_state.p, nullptr, e->eval_pi.p, e->eval_v.p,
+                                        nullptr, e->stream);
+    } else {
+        int n = e->net16.forward(e->ts.E, e->eval_count.p, e->eval_state.p, nullptr, e->eval_pi.p, e->eval_v.p,
+                                 nullptr, e->stream);
+        if (n < 0) return n;
+        e->launches += n;
+    }
+    if (e->cfg.eval_log_capacity > 0) {
+        k_log_append<<<64, 256, 0, e->stream>>>(e->ts, e->log_states.p, e->log_pi.p, e->log_v.p, e->log_count.p,
+                                                e->cfg.eval_log_capacity);
+        k_log_advance<<<1, 1, 0, e->stream>>>(e->ts, e->log_count.p);
+        e->launches += 2;
+    }
+    launch_expand_backup(e->ts, e->stream);
+    e->launches += 1;
+    return TC_OK;
+}
+
+static int check_evaluator_ready(tc_engine *e)
+{
+    if (e->evaluator == TC_EVAL_HASH) return TC_OK;
+    TC_CHECK(e->have_weights, TC_ESTATE, "network evaluator selected but tc_load_weights has not been called");
+    if (e->evaluator == TC_EVAL_NET_BF16)
+        TC_CHECK(e->net16.loaded, TC_ESTATE, "bf16 evaluator not available for this network shape: %s",
+                 e->net16.why_not.c_str());
+    return TC_OK;
+}
+
+extern "C" int tc_search(tc_engine *e, int num_sims, double cpuct)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(num_sims >= 0, TC_EINVAL, "tc_search: negative num_sims");
+    TC_TRY(check_evaluator_ready(e));
+    for (int s = 0; s < num_sims; ++s) TC_TRY(enqueue_simulation(e, cpuct));
+    TC_CUDA(cudaGetLastError());
+    return check_device_errors(e);
+}
+
+extern "C" int tc_root_counts(tc_engine *e, uint32_t *counts_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(counts_host, TC_EINVAL, "tc_root_counts: null buffer");
+    launch_root_counts(e->ts, e->counts.p, nullptr, e->stream);
+    e->launches += 1;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaMemcpyAsync(counts_host, e->counts.p, e->counts.bytes(), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    return TC_OK;
+}
+
+extern "C" int tc_root_q(tc_engine *e, double *q_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(q_host, TC_EINVAL, "tc_root_q: null buffer");
+    launch_root_counts(e->ts, nullptr, e->root_q.p, e->stream);
+    e->launches += 1;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaMemcpyAsync(q_host, e->root_q.p, e->root_q.bytes(), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    return TC_OK;
+}
+
+extern "C" int tc_get_stats(tc_engine *e, tc_stats *out)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(out, TC_EINVAL, "tc_get_stats: null output");
+    TC_CUDA(cudaMemsetAsync(e->totals.p, 0, e->totals.bytes(), e->stream));
+    k_tree_totals<<<std::min(ceil_div(e->ts.E, 256), 64), 256, 0, e->stream>>>(e->ts, e->totals.p);
+    e->launches += 1;
+    unsigned long long h[16];
+    TC_CUDA(cudaMemcpyAsync(h, e->totals.p, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    out->sims = h[0]; out->sum_depth = h[1]; out->sum_legal = h[2]; out->nn_leaves = h[3];
+    out->sum_leaf_legal = h[4]; out->terminal_leaves = h[5]; out->transpositions = h[6];
+    out->nodes_in_use = h[7]; out->edges_in_use = h[8]; out->max_nodes_one_tree = h[9]; out->max_edges_one_tree = h[10];
+    out->kernel_launches = e->launches;
+    return TC_OK;
+}
+
+extern "C" int tc_reset_stats(tc_engine *e)
+{
+    TC_TRY(check_engine(e));
+    k_zero_counters<<<ceil_div(e->ts.E, 256), 256, 0, e->stream>>>(e->ts);
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    e->launches = 0;
+    return TC_OK;
+}
+
+extern "C" int tc_eval_log(tc_engine *e, int max, uint32_t *states_host, float *pi_host, float *v_host, int *count_out)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(count_out, TC_EINVAL, "tc_eval_log: null count_out");
+    int n = 0;
+    TC_CUDA(cudaMemcpyAsync(&n, e->log_count.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    *count_out = n;
+    n = std::min(std::min(n, max), e->cfg.eval_log_capacity);
+    if (n > 0) {
+        if (states_host) TC_CUDA(cudaMemcpy(states_host, e->log_states.p, 8 * (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (pi_host) TC_CUDA(cudaMemcpy(pi_host, e->log_pi.p, 81 * (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (v_host) TC_CUDA(cudaMemcpy(v_host, e->log_v.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    return TC_OK;
+}
+
+// ---- evaluator ---------------------------------------------------------------------------------
+extern "C" size_t tc_weight_blob_floats(const tc_net_desc *desc) { return desc ? blob_floats(*desc) : 0; }
+
+extern "C" int tc_load_weights(tc_engine *e, const tc_net_desc *desc, const float *blob_host, size_t n_floats)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(desc && blob_host, TC_EINVAL, "tc_load_weights: null argument");
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    TC_TRY(fold_blob(*desc, blob_host, n_floats, e->folded));
+    TC_CHECK(desc->channels < 32 || desc->channels % 32 == 0, TC_EINVAL,
+             "channels must be < 32 or a multiple of 32, got %d", desc->channels);
+    const int cap = std::max(e->ts.E, 1);
+    TC_TRY(e->net32.upload(e->folded, cap));
+    e->net16.upload(e->folded, cap);       // optional: records why_not when the shape is unsupported
+    e->have_weights = true;
+    return TC_OK;
+}
+
+static int ensure_fwd_scratch(tc_engine *e, int batch)
+{
+    if (batch <= e->fwd_capacity) return TC_OK;
+    TC_CUDA(e->fwd_obs.alloc((size_t)batch * e->folded.d.in_planes * 81));
+    TC_CUDA(e->fwd_states.alloc((size_t)batch * 8));
+    TC_CUDA(e->fwd_pi.alloc((size_t)batch * 81));
+    TC_CUDA(e->fwd_v.alloc((size_t)batch));
+    TC_CUDA(e->fwd_logits.alloc((size_t)batch * 81));
+    e->fwd_capacity = batch;
+    return TC_OK;
+}
+
+static int run_forward(tc_engine *e, int evaluator, int batch, const uint32_t *states_dev, const float *obs_dev,
+                       float *pi_dev, float *v_dev, float *logits_dev)
+{
+    TC_CHECK(e->have_weights, TC_ESTATE, "tc_forward: tc_load_weights has not been called");
+    TC_CHECK(evaluator == TC_EVAL_NET_F32 || evaluator == TC_EVAL_NET_BF16, TC_EINVAL,
+             "tc_forward: evaluator must be TC_EVAL_NET_F32 or TC_EVAL_NET_BF16");
+    TC_CHECK(states_dev == nullptr || e->folded.d.in_planes == 4, TC_EINVAL,
+             "packed positions imply 4 input planes, the loaded network has %d", e->folded.d.in_planes);
+    // the network scratch is sized for num_envs rows: run larger batches in slices
+    const int cap = e->net32.capacity;
+    for (int r0 = 0; r0 < batch; r0 += cap) {
+        const int nb = std::min(cap, batch - r0);
+        const uint32_t *s = states_dev ? states_dev + (size_t)r0 * 8 : nullptr;
+        const float *o = obs_dev ? obs_dev + (size_t)r0 * e->folded.d.in_planes * 81 : nullptr;
+        float *lg = logits_dev ? logits_dev + (size_t)r0 * 81 : nullptr;
+        if (evaluator == TC_EVAL_NET_F32) {
+            e->launches += e->net32.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream);
+        } else {
+            TC_CHECK(e->net16.loaded, TC_ESTATE, "bf16 evaluator not available for this network shape: %s",
+                     e->net16.why_not.c_str());
+            int n = e->net16.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream);
+            if (n < 0) return n;
+            e->launches += n;
+        }
+    }
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+extern "C" int tc_forward(tc_engine *e, int evaluator, int batch, const float *obs_host, float *pi_host, float *v_host,
+                          float *logits_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(batch >= 0 && (batch == 0 || (obs_host && pi_host && v_host)), TC_EINVAL, "tc_forward: null buffer");
+    if (batch == 0) return TC_OK;
+    TC_CHECK(e->have_weights, TC_ESTATE, "tc_forward: tc_load_weights has not been called");
+    TC_TRY(ensure_fwd_scratch(e, batch));
+    const size_t in_floats = (size_t)batch * e->folded.d.in_planes * 81;
+    TC_CUDA(cudaMemcpyAsync(e->fwd_obs.p, obs_host, in_floats * 4, cudaMemcpyHostToDevice, e->stream));
+    TC_TRY(run_forward(e, evaluator, batch, nullptr, e->fwd_obs.p, e->fwd_pi.p, e->fwd_v.p,
+                       logits_host ? e->fwd_logits.p : nullptr));
+    TC_CUDA(cudaMemcpyAsync(pi_host, e->fwd_pi.p, (size_t)batch * 81 * 4, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaMemcpyAsync(v_host, e->fwd_v.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (logits_host)
+        TC_CUDA(cudaMemcpyAsync(logits_host, e->fwd_logits.p, (size_t)batch * 81 * 4, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    return TC_OK;
+}
+
+extern "C" int tc_forward_states(tc_engine *e, int evaluator, int batch, const uint32_t *states_host, float *pi_host,
+                                 float *v_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(batch >= 0 && (batch == 0 || (states_host && pi_host && v_host)), TC_EINVAL,
+             "tc_forward_states: null buffer");
+    if (batch == 0) return TC_OK;
+    TC_CHECK(e->have_weights, TC_ESTATE, "tc_forward_states: tc_load_weights has not been called");
+    TC_TRY(ensure_fwd_scratch(e, batch));
+    TC_CUDA(cudaMemcpyAsync(e->fwd_states.p, states_host, (size_t)batch * 32, cudaMemcpyHostToDevice, e->stream));
+    TC_TRY(run_forward(e, evaluator, batch, e->fwd_states.p, nullptr, e->fwd_pi.p, e->fwd_v.p, nullptr));
+    TC_CUDA(cudaMemcpyAsync(pi_host, e->fwd_pi.p, (size_t)batch * 81 * 4, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaMemcpyAsync(v_host, e->fwd_v.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    return TC_OK;
+}
+
+extern "C" int tc_forward_states_dev(tc_engine *e, int evaluator, int batch, const uint32_t *states_dev, float *pi_dev,
+                                     float *v_dev)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(batch >= 0 && (batch == 0 || (states_dev && pi_dev && v_dev)), TC_EINVAL,
+             "tc_forward_states_dev: null buffer");
+    if (batch == 0) return TC_OK;
+    return run_forward(e, evaluator, batch, states_dev, nullptr, pi_dev, v_dev, nullptr);
+}
+
+// ---- self-play driver --------------------------------------------------------------------------
+extern "C" int tc_selfplay_begin(tc_engine *e, const tc_selfplay_config *cfg)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(cfg && cfg->num_sims >= 1 && cfg->temp_threshold >= 0, TC_EINVAL, "tc_selfplay_begin: bad config");
+    TC_TRY(check_evaluator_ready(e));
+    const size_t E = e->ts.E;
+    if (!e->sp_ready) {
+        TC_CUDA(e->sp_env.alloc(E));
+        TC_CUDA(e->sp_pending.alloc(E * 81));
+        TC_CUDA(e->sp_finished.alloc(E * 96));
+        TC_CUDA(e->sp_finished_count.alloc(1));
+        TC_CUDA(e->sp_stats.alloc(8));
+        e->sp.E = (int)E;
+        e->sp.env = e->sp_env.p;
+        e->sp.pending = e->sp_pending.p;
+        e->sp.finished = e->sp_finished.p;
+        e->sp.finished_cap = (int)(E * 96);
+        e->sp.finished_count = e->sp_finished_count.p;
+        e->sp.stats = e->sp_stats.p;
+        e->sp.root_states = e->root_states.p;
+        e->sp.root_active = e->root_active.p;
+        e->sp_ready = true;
+    }
+    e->sp_cfg = *cfg;
+    launch_selfplay_init(e->sp, e->stream);
+    launch_reset(e->ts, -1, e->stream);
+    e->launches += 2;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+extern "C" int tc_selfplay_step(tc_engine *e, int plies)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(e->sp_ready, TC_ESTATE, "tc_selfplay_step before tc_selfplay_begin");
+    TC_CHECK(plies >= 0, TC_EINVAL, "negative plies");
+    for (int p = 0; p < plies; ++p) {
+        launch_selfplay_roots(e->sp, e->stream);
+        launch_set_roots(e->ts, e->root_states.p, e->root_active.p, e->stream);
+        e->launches += 2;
+        for (int s = 0; s < e->sp_cfg.num_sims; ++s) TC_TRY(enqueue_simulation(e, e->sp_cfg.cpuct));
+        launch_selfplay_move(e->ts, e->sp, e->sp_cfg, e->stream);
+        e->launches += 1;
+        if (e->sp_cfg.auto_reset) {
+            launch_reset_marked(e->ts, e->sp, e->stream);
+            e->launches += 1;
+        }
+    }
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+extern "C" int tc_selfplay_sync(tc_engine *e)
+{
+    TC_TRY(check_engine(e));
+    return check_device_errors(e);
+}
+
+extern "C" int tc_selfplay_get_stats(tc_engine *e, tc_selfplay_stats *out)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(out && e->sp_ready, TC_ESTATE, "tc_selfplay_get_stats before tc_selfplay_begin");
+    unsigned long long h[8];
+    int nfin = 0;
+    TC_CUDA(cudaMemcpyAsync(h, e->sp_stats.p, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaMemcpyAsync(&nfin, e->sp_finished_count.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    out->plies = h[0]; out->sims = h[1]; out->games_finished = h[2];
+    out->first_player_wins = h[3]; out->second_player_wins = h[4]; out->draws = h[5];
+    out->examples = (uint64_t)std::min(nfin, e->sp.finished_cap);
+    return TC_OK;
+}
+
+static int drain_common(tc_engine *e, int max, tc_example *out, bool to_host, int *count_out)
+{
+    TC_CHECK(e->sp_ready, TC_ESTATE, "tc_selfplay_drain before tc_selfplay_begin");
+    TC_CHECK(count_out && (max == 0 || out), TC_EINVAL, "tc_selfplay_drain: null argument");
+    int nfin = 0;
+    unsigned long long dropped = 0;
+    TC_CUDA(cudaMemcpyAsync(&nfin, e->sp_finished_count.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaMemcpyAsync(&dropped, e->sp_stats.p + 6, sizeof dropped, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    TC_CHECK(dropped == 0, TC_ECAPACITY, "self-play record buffer overflowed: %llu records dropped; drain more often",
+             dropped);
+    TC_CHECK(nfin <= max, TC_EINVAL, "tc_selfplay_drain: %d records pending, buffer holds %d", nfin, max);
+    if (nfin > 0)
+        TC_CUDA(cudaMemcpyAsync(out, e->sp_finished.p, (size_t)nfin * sizeof(tc_example),
+                                to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->stream));
+    TC_CUDA(cudaMemsetAsync(e->sp_finished_count.p, 0, sizeof(int), e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    *count_out = nfin;
+    return TC_OK;
+}
+
+extern "C" int tc_selfplay_drain(tc_engine *e, int max, tc_example *out_host, int *count_out)
+{
+    TC_TRY(check_engine(e));
+    return drain_common(e, max, out_host, true, count_out);
+}
+
+extern "C" int tc_selfplay_drain_dev(tc_engine *e, int max, tc_example *out_dev, int *count_out)
+{
+    TC_TRY(check_engine(e));
+    return drain_common(e, max, out_dev, false, count_out);
+}

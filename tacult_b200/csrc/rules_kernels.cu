@@ -1,0 +1,204 @@
+// Rules-engine entry points of the C ABI: batched make-move, legal mask, terminal status,
+// observation planes and seeded playouts, all as bit-parallel integer kernels.
+// Reference call sites replaced: /root/reference/src/tacult/utac_game.py:34-107,247-250 and
+// /root/reference/src/tacult/base/utils.py:7-10 (which reach the external C++ `utac`).
+#include "common.cuh"
+#include "rules.cuh"
+
+namespace tc {
+
+__global__ void k_rules_step(int n, const uint32_t *__restrict__ in, const int8_t *__restrict__ actions,
+                             uint32_t *__restrict__ out, int8_t *__restrict__ status, int *__restrict__ illegal)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    const uint4 *src = reinterpret_cast<const uint4 *>(in + 8 * (size_t)i);
+    uint4 a0 = src[0], a1 = src[1];
+    w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+    Pos p = unpack(w);
+    Summary s = summarize(p);
+    uint32_t legal[3];
+    legal_words(p, s, legal);
+    int a = actions[i];
+    if (a < 0 || a > 80 || !action_bit(legal, a)) {
+        atomicAdd(illegal, 1);
+        pack(p, w);
+        status[i] = (int8_t)status_of(s);
+    } else {
+        Pos q = play(p, a);
+        pack(q, w);
+        status[i] = (int8_t)status_of(summarize(q));
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(out + 8 * (size_t)i);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// one warp per position: lane l owns actions l, l+32, l+64
+__global__ void k_rules_mask_obs(int n, const uint32_t *__restrict__ in, uint8_t *__restrict__ mask,
+                                 float *__restrict__ obs, int8_t *__restrict__ status)
+{
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = in[8 * (size_t)warp + k];
+    Pos p = unpack(w);
+    Summary s = summarize(p);
+    uint32_t legal[3];
+    legal_words(p, s, legal);
+    if (status && lane == 0) status[warp] = (int8_t)status_of(s);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int a = lane + 32 * q;
+        if (a < 81) {
+            bool lg = action_bit(legal, a);
+            if (mask) mask[81 * (size_t)warp + a] = lg ? 1 : 0;
+            if (obs) {
+                bool mine = action_bit(p.mine, a), occ = action_bit(p.occ, a);
+                float *o = obs + 324 * (size_t)warp;
+                o[a] = mine ? 1.f : 0.f;
+                o[81 + a] = (occ && !mine) ? 1.f : 0.f;
+                o[162 + a] = lg ? 1.f : 0.f;
+                o[243 + a] = 1.f;               // canonical frame: side == 1 (utac_game.py:106)
+            }
+        }
+    }
+}
+
+// one thread per game; same specification as oracle/utac_rules.c:utac_playout
+__global__ void k_rules_playouts(uint64_t seed, uint64_t first_game, int n, int max_plies,
+                                 tc_playout_result *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t game = first_game + (uint64_t)i;
+    Pos p;
+    p.mine[0] = p.mine[1] = p.mine[2] = 0;
+    p.occ[0] = p.occ[1] = p.occ[2] = 0;
+    p.last = 0;
+    uint64_t sum = mix64(seed ^ game);
+    int ply = 0, outcome = 0;
+    int first_to_move = 1;
+    Summary s = summarize(p);
+    while (ply < max_plies && status_of(s) == 0) {
+        uint32_t lw[3], am[3];
+        legal_words(p, s, lw);
+        to_action_order(lw, am);
+        int nl = popc32(am[0]) + popc32(am[1]) + popc32(am[2]);
+        uint64_t r = mix64(seed ^ (game * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)ply * 0xD1B54A32D192ED03ull));
+        int a = nth_action(am, (int)(r % (uint64_t)nl));
+        p = play(p, a);
+        s = summarize(p);
+        first_to_move = -first_to_move;
+        ++ply;
+        uint32_t w[8];
+        pack(p, w);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum = mix64(sum ^ w[k]);
+        legal_words(p, s, lw);
+        to_action_order(lw, am);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sum = mix64(sum ^ am[k]);
+        int st = status_of(s);
+        if (st == 3) outcome = first_to_move;
+        if (st == 1) outcome = -first_to_move;
+        sum = mix64(sum ^ (uint32_t)st);
+    }
+    tc_playout_result res;
+    res.checksum = sum;
+    res.plies = ply;
+    res.outcome = outcome;
+    uint32_t w[8];
+    pack(p, w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) res.final_state[k] = w[k];
+    out[i] = res;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+extern "C" int tc_rules_step(int n, const uint32_t *states_host, const int8_t *actions_host,
+                             uint32_t *out_states_host, int8_t *status_host)
+{
+    TC_CHECK(n >= 0 && (n == 0 || (states_host && actions_host && out_states_host && status_host)), TC_EINVAL,
+             "tc_rules_step: null buffer");
+    if (n == 0) return TC_OK;
+    DevBuf<uint32_t> in, out;
+    DevBuf<int8_t> act, st;
+    DevBuf<int> bad;
+    TC_CUDA(in.alloc(8 * (size_t)n));
+    TC_CUDA(out.alloc(8 * (size_t)n));
+    TC_CUDA(act.alloc(n));
+    TC_CUDA(st.alloc(n));
+    TC_CUDA(bad.alloc(1));
+    TC_CUDA(cudaMemcpy(in.p, states_host, in.bytes(), cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemcpy(act.p, actions_host, act.bytes(), cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemset(bad.p, 0, sizeof(int)));
+    k_rules_step<<<ceil_div(n, 256), 256>>>(n, in.p, act.p, out.p, st.p, bad.p);
+    TC_CUDA(cudaGetLastError());
+    int nbad = 0;
+    TC_CUDA(cudaMemcpy(out_states_host, out.p, out.bytes(), cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemcpy(status_host, st.p, st.bytes(), cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemcpy(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+    TC_CHECK(nbad == 0, TC_EILLEGAL, "tc_rules_step: %d illegal move(s) requested", nbad);
+    return TC_OK;
+}
+
+static int mask_obs_common(int n, const uint32_t *states_host, uint8_t *mask_host, float *obs_host,
+                           int8_t *status_host)
+{
+    TC_CHECK(n >= 0 && (n == 0 || states_host), TC_EINVAL, "rules hook: null states");
+    if (n == 0) return TC_OK;
+    DevBuf<uint32_t> in;
+    DevBuf<uint8_t> mask;
+    DevBuf<float> obs;
+    DevBuf<int8_t> st;
+    TC_CUDA(in.alloc(8 * (size_t)n));
+    if (mask_host) TC_CUDA(mask.alloc(81 * (size_t)n));
+    if (obs_host) TC_CUDA(obs.alloc(324 * (size_t)n));
+    if (status_host) TC_CUDA(st.alloc(n));
+    TC_CUDA(cudaMemcpy(in.p, states_host, in.bytes(), cudaMemcpyHostToDevice));
+    int threads = 256, warps_per_block = threads / 32;
+    k_rules_mask_obs<<<ceil_div(n, warps_per_block), threads>>>(n, in.p, mask.p, obs.p, st.p);
+    TC_CUDA(cudaGetLastError());
+    if (mask_host) TC_CUDA(cudaMemcpy(mask_host, mask.p, mask.bytes(), cudaMemcpyDeviceToHost));
+    if (obs_host) TC_CUDA(cudaMemcpy(obs_host, obs.p, obs.bytes(), cudaMemcpyDeviceToHost));
+    if (status_host) TC_CUDA(cudaMemcpy(status_host, st.p, st.bytes(), cudaMemcpyDeviceToHost));
+    return TC_OK;
+}
+
+extern "C" int tc_rules_legal_mask(int n, const uint32_t *states_host, uint8_t *mask_host)
+{
+    TC_CHECK(n == 0 || mask_host, TC_EINVAL, "tc_rules_legal_mask: null output");
+    return mask_obs_common(n, states_host, mask_host, nullptr, nullptr);
+}
+
+extern "C" int tc_rules_status(int n, const uint32_t *states_host, int8_t *status_host)
+{
+    TC_CHECK(n == 0 || status_host, TC_EINVAL, "tc_rules_status: null output");
+    return mask_obs_common(n, states_host, nullptr, nullptr, status_host);
+}
+
+extern "C" int tc_rules_encode_obs(int n, const uint32_t *states_host, float *obs_host)
+{
+    TC_CHECK(n == 0 || obs_host, TC_EINVAL, "tc_rules_encode_obs: null output");
+    return mask_obs_common(n, states_host, nullptr, obs_host, nullptr);
+}
+
+extern "C" int tc_rules_playouts(uint64_t seed, uint64_t first_game, int n, int max_plies,
+                                 tc_playout_result *out_host)
+{
+    TC_CHECK(n >= 0 && (n == 0 || out_host), TC_EINVAL, "tc_rules_playouts: null output");
+    if (n == 0) return TC_OK;
+    DevBuf<tc_playout_result> out;
+    TC_CUDA(out.alloc(n));
+    k_rules_playouts<<<ceil_div(n, 128), 128>>>(seed, first_game, n, max_plies, out.p);
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaMemcpy(out_host, out.p, out.bytes(), cudaMemcpyDeviceToHost));
+    return TC_OK;
+}

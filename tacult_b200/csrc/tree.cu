@@ -1,0 +1,548 @@
+// Warp-per-tree PUCT selection, leaf expansion and backup (see tree.cuh for layout and citations).
+#include "tree.cuh"
+
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// small warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t key_hash(const Pos &p)
+{
+    uint64_t k0 = (uint64_t)p.mine[0] | ((uint64_t)p.mine[1] << 32);
+    uint64_t k1 = (uint64_t)p.mine[2] | ((uint64_t)p.occ[0] << 32);
+    uint64_t k2 = (uint64_t)p.occ[1] | ((uint64_t)p.occ[2] << 32);
+    return mix64(k0 ^ mix64(k1 ^ mix64(k2 ^ mix64((uint64_t)p.last))));
+}
+
+__device__ __forceinline__ void unpack_hdr(const uint4 &h0, const uint4 &h1, Pos &p, uint32_t &n_edges,
+                                           uint32_t &edge_off)
+{
+    p.mine[0] = h0.x; p.mine[1] = h0.y; p.mine[2] = h0.z;
+    p.occ[0] = h0.w;  p.occ[1] = h1.x;  p.occ[2] = h1.y;
+    p.last = h1.z & 0xFu;
+    n_edges = (h1.z >> 8) & 0xFFu;
+    edge_off = h1.w;
+}
+
+// action-order legal mask of a position, built with three ballots (lane l owns actions l, l+32, l+64)
+__device__ __forceinline__ void warp_legal_mask(const Pos &p, int lane, uint32_t am[3], int &status)
+{
+    Summary s = summarize(p);
+    status = status_of(s);
+    uint32_t lw[3];
+    legal_words(p, s, lw);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int a = lane + 32 * q;
+        bool lg = (a < 81) && action_bit(lw, a);
+        am[q] = __ballot_sync(FULL, lg);
+    }
+}
+
+__device__ __forceinline__ int edge_index(const uint32_t am[3], int q, int lane)
+{
+    int j = __popc(am[q] & ((1u << lane) - 1u));
+    if (q >= 1) j += __popc(am[0]);
+    if (q >= 2) j += __popc(am[1]);
+    return j;
+}
+
+struct EdgeBlock {
+    double *P;
+    double *Q;
+    uint32_t *N;
+    uint32_t *child;
+};
+
+__device__ __forceinline__ EdgeBlock edge_block(const TreeStore &ts, int tree, uint32_t edge_off, uint32_t n)
+{
+    unsigned long long *base = ts.edge_mem + 3ull * ((unsigned long long)tree * ts.capE + edge_off);
+    EdgeBlock b;
+    b.P = reinterpret_cast<double *>(base);
+    b.Q = b.P + n;
+    b.N = reinterpret_cast<uint32_t *>(b.Q + n);
+    b.child = b.N + n;
+    return b;
+}
+
+// Looks the position up in the tree's table.  Returns the node index or -1; when absent `free_slot`
+// is where it would be inserted (0xFFFFFFFF if the table is full).
+__device__ int table_find(const TreeStore &ts, int tree, const Pos &p, uint64_t h, int lane, uint32_t &free_slot)
+{
+    const uint32_t mask = ts.hashSize - 1u;
+    const uint32_t *table = ts.hash + (size_t)tree * ts.hashSize;
+    const uint4 *hdr = ts.node_hdr + 2ull * (size_t)tree * ts.capN;
+    const uint32_t tag = (uint32_t)(h >> 40) & 0xFFFu;
+    const uint32_t start = (uint32_t)h & mask;
+    for (uint32_t probe = 0; probe < ts.hashSize; probe += 32) {
+        uint32_t slot = (start + probe + (uint32_t)lane) & mask;
+        uint32_t e = table[slot];
+        unsigned empties = __ballot_sync(FULL, e == 0u);
+        unsigned cands = __ballot_sync(FULL, e != 0u && (e >> 20) == tag);
+        int first_empty = empties ? (__ffs(empties) - 1) : 32;
+        if (first_empty < 32) cands &= (1u << first_empty) - 1u;
+        while (cands) {
+            int src = __ffs(cands) - 1;
+            cands &= cands - 1u;
+            uint32_t ce = __shfl_sync(FULL, e, src);
+            uint32_t idx = (ce & 0xFFFFFu) - 1u;
+            uint4 h0 = hdr[2ull * idx], h1 = hdr[2ull * idx + 1];
+            if (h0.x == p.mine[0] && h0.y == p.mine[1] && h0.z == p.mine[2] && h0.w == p.occ[0] &&
+                h1.x == p.occ[1] && h1.y == p.occ[2] && (h1.z & 0xFu) == p.last)
+                return (int)idx;
+        }
+        if (first_empty < 32) {
+            free_slot = (start + probe + (uint32_t)first_empty) & mask;
+            return -1;
+        }
+    }
+    free_slot = 0xFFFFFFFFu;
+    return -1;
+}
+
+// Creates a node for `p` (n legal moves, action mask am) and requests its evaluation.
+// Returns the node index, or -1 if a pool is exhausted (error flag raised, tree parked).
+__device__ int create_leaf(const TreeStore &ts, int tree, TreeCtl &c, const Pos &p, uint64_t h, uint32_t free_slot,
+                           const uint32_t am[3], int lane)
+{
+    uint32_t n = (uint32_t)(__popc(am[0]) + __popc(am[1]) + __popc(am[2]));
+    if (c.n_nodes >= ts.capN || c.n_edges + n > ts.capE || free_slot == 0xFFFFFFFFu) {
+        if (lane == 0) atomicExch(ts.error_flag, 1);
+        c.active = 0;
+        return -1;
+    }
+    uint32_t idx = c.n_nodes++;
+    uint32_t off = c.n_edges;
+    c.n_edges += n;
+    size_t g = (size_t)tree * ts.capN + idx;
+    if (lane == 0) {
+        ts.node_hdr[2 * g] = make_uint4(p.mine[0], p.mine[1], p.mine[2], p.occ[0]);
+        ts.node_hdr[2 * g + 1] = make_uint4(p.occ[1], p.occ[2], p.last | (n << 8), off);
+        ts.node_Ns[g] = 0u;
+        ts.hash[(size_t)tree * ts.hashSize + free_slot] = (((uint32_t)(h >> 40) & 0xFFFu) << 20) | (idx + 1u);
+    }
+    EdgeBlock eb = edge_block(ts, tree, off, n);
+    for (uint32_t j = lane; j < n; j += 32) {
+        eb.N[j] = 0u;
+        eb.child[j] = CHILD_UNRESOLVED;
+    }
+    int row = 0;
+    if (lane == 0) row = atomicAdd(ts.eval_count, 1);
+    row = __shfl_sync(FULL, row, 0);
+    if (lane < 8) {
+        uint32_t w = lane == 0 ? p.mine[0] : lane == 1 ? p.mine[1] : lane == 2 ? p.mine[2] : lane == 3 ? p.occ[0]
+                   : lane == 4 ? p.occ[1] : lane == 5 ? p.occ[2] : lane == 6 ? p.last : 0u;
+        ts.eval_state[8 * (size_t)row + lane] = w;
+    }
+    c.leaf_kind = LEAF_NN;
+    c.leaf_node = (int)idx;
+    c.leaf_row = row;
+    c.nn_leaves += 1;
+    c.sum_leaf_legal += n;
+    return (int)idx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_fields(int n, const uint16_t *__restrict__ board, const uint16_t *__restrict__ occ,
+                              const int8_t *__restrict__ last, uint32_t *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        w[g] = 0; w[3 + g] = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            w[g] |= ((uint32_t)board[9 * (size_t)i + 3 * g + j] & F9) << (9 * j);
+            w[3 + g] |= ((uint32_t)occ[9 * (size_t)i + 3 * g + j] & F9) << (9 * j);
+        }
+    }
+    w[6] = (uint32_t)((int)last[i] + 1) & 0xFu;
+    w[7] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[8 * (size_t)i + k] = w[k];
+}
+
+__global__ void k_reset(TreeStore ts, int env)
+{
+    // one block per tree: clear the hash table and the control block
+    int tree = env >= 0 ? env : (int)blockIdx.x;
+    uint32_t *table = ts.hash + (size_t)tree * ts.hashSize;
+    for (uint32_t i = threadIdx.x; i < ts.hashSize; i += blockDim.x) table[i] = 0u;
+    if (threadIdx.x == 0) {
+        TreeCtl *c = ts.ctl + tree;          // the §8(d) counters survive a reset (tc_reset_stats clears them)
+        memset(c->root_state, 0, sizeof c->root_state);
+        c->root_idx = -1;
+        c->active = 0;
+        c->n_nodes = 0;
+        c->n_edges = 0;
+        c->leaf_kind = LEAF_NONE;
+        c->leaf_node = -1;
+        c->leaf_row = 0;
+        c->path_len = 0;
+        c->leaf_value = 0.0;
+    }
+}
+
+__global__ void k_set_roots(TreeStore ts, const uint32_t *__restrict__ states, const uint8_t *__restrict__ active)
+{
+    int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (tree >= ts.E) return;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = states[8 * (size_t)tree + k];
+    Pos p = unpack(w);
+    int status = status_of(summarize(p));
+    bool on = (active == nullptr || active[tree] != 0) && status == 0;
+    uint32_t free_slot;
+    int idx = -1;
+    if (on) idx = table_find(ts, tree, p, key_hash(p), lane, free_slot);
+    if (lane == 0) {
+        TreeCtl *c = ts.ctl + tree;
+        uint32_t packed[8];
+        pack(p, packed);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c->root_state[k] = packed[k];
+        c->root_idx = idx;
+        c->active = on ? 1 : 0;
+        c->leaf_kind = LEAF_NONE;
+        c->path_len = 0;
+    }
+}
+
+// One simulation's descent for every tree: mcts.py:243-325 (selection part of `_search`).
+__global__ void __launch_bounds__(128) k_select(TreeStore ts, double cpuct)
+{
+    int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (tree >= ts.E) return;
+    TreeCtl c = ts.ctl[tree];
+    c.leaf_kind = LEAF_NONE;
+    c.path_len = 0;
+    if (!c.active) {
+        if (lane == 0) { ts.ctl[tree].leaf_kind = LEAF_NONE; ts.ctl[tree].path_len = 0; }
+        return;
+    }
+    c.sims += 1;
+    uint4 *path = ts.path + (size_t)tree * MAX_DEPTH;
+    const uint4 *hdr = ts.node_hdr + 2ull * (size_t)tree * ts.capN;
+    const uint32_t *nodeNs = ts.node_Ns + (size_t)tree * ts.capN;
+
+    if (c.root_idx < 0) {
+        // root never expanded: it is this simulation's leaf (mcts.py:268-290 at recursion depth 0)
+        Pos p = unpack(c.root_state);
+        uint32_t am[3];
+        int status;
+        warp_legal_mask(p, lane, am, status);
+        uint64_t h = key_hash(p);
+        uint32_t free_slot;
+        int idx = table_find(ts, tree, p, h, lane, free_slot);
+        if (idx < 0) idx = create_leaf(ts, tree, c, p, h, free_slot, am, lane);
+        c.root_idx = idx;
+    } else {
+        int cur = c.root_idx;
+        int depth = 0;
+        while (true) {
+            uint4 h0 = hdr[2ull * cur], h1 = hdr[2ull * cur + 1];
+            Pos p;
+            uint32_t n, off;
+            unpack_hdr(h0, h1, p, n, off);
+            uint32_t ns = nodeNs[cur];
+            uint32_t am[3];
+            int status;
+            warp_legal_mask(p, lane, am, status);
+            EdgeBlock eb = edge_block(ts, tree, off, n);
+
+            // PUCT over the legal edges (mcts.py:301-316); lane l scores actions l, l+32, l+64
+            const double sq_visited = __dsqrt_rn((double)ns);
+            const double sq_fresh = __dsqrt_rn(__dadd_rn((double)ns, 1e-8));
+            double best_u = -INFINITY;
+            int best_a = 1 << 20, best_j = -1;
+            double pj[3], qj[3];
+            uint32_t nj[3];
+            int jj[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                jj[q] = -1;
+                if ((am[q] >> lane) & 1u) {
+                    int j = edge_index(am, q, lane);
+                    jj[q] = j;
+                    pj[q] = eb.P[j];
+                    qj[q] = eb.Q[j];
+                    nj[q] = eb.N[j];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (jj[q] >= 0) {
+                    double cp = __dmul_rn(cpuct, pj[q]);
+                    double u = nj[q] ? __dadd_rn(qj[q], __ddiv_rn(__dmul_rn(cp, sq_visited), (double)(1u + nj[q])))
+                                     : __dmul_rn(cp, sq_fresh);
+                    if (u > best_u) { best_u = u; best_a = lane + 32 * q; best_j = jj[q]; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                double ou = __shfl_xor_sync(FULL, best_u, d);
+                int oa = __shfl_xor_sync(FULL, best_a, d);
+                int oj = __shfl_xor_sync(FULL, best_j, d);
+                // a lane that found nothing carries best_j == -1 and never wins
+                bool take = (oj >= 0) && (best_j < 0 || ou > best_u || (ou == best_u && oa < best_a));
+                if (take) { best_u = ou; best_a = oa; best_j = oj; }
+            }
+            c.sum_depth += 1;
+            c.sum_legal += n;
+            if (best_j < 0) {           // cannot happen for a live position; park the tree loudly
+                if (lane == 0) atomicExch(ts.error_flag, 2);
+                c.active = 0;
+                c.path_len = 0;
+                break;
+            }
+            if (lane == 0) path[depth] = make_uint4((uint32_t)cur, off, (uint32_t)best_j | (n << 8), (uint32_t)best_a);
+            ++depth;
+            c.path_len = depth;
+
+            uint32_t child = eb.child[best_j];
+            if (child >= CHILD_TERM_BASE && child != CHILD_UNRESOLVED) {
+                int st = (int)(child - CHILD_TERM_BASE);
+                c.leaf_kind = LEAF_TERMINAL;
+                c.leaf_value = st == 2 ? 1e-4 : (st == 3 ? 1.0 : -1.0);   // utac_game.py:64-81
+                c.terminal_leaves += 1;
+                break;
+            }
+            if (child != CHILD_UNRESOLVED) { cur = (int)child; continue; }
+
+            // first traversal of this edge: successor position (mcts.py:319-320)
+            Pos nx = play(p, best_a);
+            uint32_t nam[3];
+            int nst;
+            warp_legal_mask(nx, lane, nam, nst);
+            if (nst != 0) {
+                if (lane == 0) eb.child[best_j] = CHILD_TERM_BASE + (uint32_t)nst;
+                c.leaf_kind = LEAF_TERMINAL;
+                c.leaf_value = nst == 2 ? 1e-4 : (nst == 3 ? 1.0 : -1.0);
+                c.terminal_leaves += 1;
+                break;
+            }
+            uint64_t h = key_hash(nx);
+            uint32_t free_slot;
+            int idx = table_find(ts, tree, nx, h, lane, free_slot);
+            if (idx >= 0) {             // transposition: the position is already a node (mcts.py:268 is false)
+                if (lane == 0) eb.child[best_j] = (uint32_t)idx;
+                c.transpositions += 1;
+                cur = idx;
+                continue;
+            }
+            idx = create_leaf(ts, tree, c, nx, h, free_slot, nam, lane);
+            if (idx >= 0) {
+                if (lane == 0) eb.child[best_j] = (uint32_t)idx;
+            } else {
+                c.path_len = 0;         // pool exhausted: drop this simulation
+                c.leaf_kind = LEAF_NONE;
+            }
+            break;
+        }
+    }
+    if (lane == 0) ts.ctl[tree] = c;
+}
+
+// numpy's float64 np.sum over 81 contiguous values (8 running sums, pairwise tree, tail), mcts.py:273
+__device__ __forceinline__ double numpy_sum81(const double x[3], int lane)
+{
+    const int j8 = lane & 7;
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        // element a = 8k + j8 (< 80) lives in x[a / 32] of lane a % 32; a / 32 == k / 4 because j8 < 8
+        double v = __shfl_sync(FULL, x[k >> 2], 8 * (k & 3) + j8);
+        r = (k == 0) ? v : __dadd_rn(r, v);
+    }
+    double r0 = __shfl_sync(FULL, r, 0), r1 = __shfl_sync(FULL, r, 1), r2 = __shfl_sync(FULL, r, 2),
+           r3 = __shfl_sync(FULL, r, 3), r4 = __shfl_sync(FULL, r, 4), r5 = __shfl_sync(FULL, r, 5),
+           r6 = __shfl_sync(FULL, r, 6), r7 = __shfl_sync(FULL, r, 7);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    double tail = __shfl_sync(FULL, x[2], 16);      // element 80
+    return __dadd_rn(res, tail);
+}
+
+// Expansion of the evaluated leaf (mcts.py:268-290) and backup along the path (mcts.py:327-341).
+__global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
+{
+    int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (tree >= ts.E) return;
+    const TreeCtl *cp = ts.ctl + tree;
+    int kind = cp->leaf_kind;
+    if (kind == LEAF_NONE) return;
+    int path_len = cp->path_len;
+    double x;
+    if (kind == LEAF_NN) {
+        int node = cp->leaf_node, row = cp->leaf_row;
+        const uint4 *hdr = ts.node_hdr + 2ull * ((size_t)tree * ts.capN + node);
+        Pos p;
+        uint32_t n, off;
+        unpack_hdr(hdr[0], hdr[1], p, n, off);
+        uint32_t am[3];
+        int status;
+        warp_legal_mask(p, lane, am, status);
+        const float *pi = ts.eval_pi + 81 * (size_t)row;
+        double m[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            int a = lane + 32 * q;
+            m[q] = 0.0;
+            if (a < 81 && ((am[q] >> lane) & 1u)) m[q] = (double)pi[a];
+        }
+        double total = numpy_sum81(m, lane);
+        EdgeBlock eb = edge_block(ts, tree, off, n);
+        const bool ok = total > 0.0;
+        const double uniform = __ddiv_rn(1.0, (double)n);     // (0 + valids) / np.sum(valids), mcts.py:282-283
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if ((am[q] >> lane) & 1u) {
+                int j = edge_index(am, q, lane);
+                eb.P[j] = ok ? __ddiv_rn(m[q], total) : uniform;
+            }
+        }
+        x = (double)ts.eval_v[row];
+    } else {
+        x = cp->leaf_value;
+    }
+    // edge `dist` levels above the leaf receives 0.0 + -(value one level below)  (mcts.py:325,342)
+    const uint4 *path = ts.path + (size_t)tree * MAX_DEPTH;
+    uint32_t *nodeNs = ts.node_Ns + (size_t)tree * ts.capN;
+    for (int e = lane; e < path_len; e += 32) {
+        uint4 pe = path[e];
+        int dist = path_len - e;
+        double v = (dist & 1) ? -x : x;
+        v = __dadd_rn(0.0, v);                                  // -0.0 normalises to +0.0 as in the reference
+        uint32_t n = pe.z >> 8, j = pe.z & 0xFFu;
+        EdgeBlock eb = edge_block(ts, tree, pe.y, n);
+        uint32_t cnt = eb.N[j];
+        double q = v;
+        if (cnt) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)cnt, eb.Q[j]), v), (double)(cnt + 1u));
+        eb.Q[j] = q;
+        eb.N[j] = cnt + 1u;
+        nodeNs[pe.x] += 1u;
+    }
+}
+
+// Deterministic evaluator, specification in oracle/evaluators.py (HashEvaluator)
+__global__ void k_hash_eval(TreeStore ts, HashEvalParams hp)
+{
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= *ts.eval_count) return;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = ts.eval_state[8 * (size_t)row + k];
+    Pos p = unpack(w);
+    uint32_t am[3];
+    int status;
+    warp_legal_mask(p, lane, am, status);
+    uint64_t h = mix64(hp.salt);
+    h = mix64(h ^ p.mine[0]); h = mix64(h ^ p.mine[1]); h = mix64(h ^ p.mine[2]);
+    h = mix64(h ^ p.occ[0]);  h = mix64(h ^ p.occ[1]);  h = mix64(h ^ p.occ[2]);
+    h = mix64(h ^ am[0]);     h = mix64(h ^ am[1]);     h = mix64(h ^ am[2]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int a = lane + 32 * q;
+        if (a < 81) {
+            uint64_t r = mix64(h ^ ((uint64_t)(a + 1) * 0x9E3779B97F4A7C15ull));
+            float v;
+            if (hp.pi_levels == 0) v = (float)((uint32_t)(r >> 40) + 1u) * 5.9604644775390625e-08f;   // 2^-24
+            else v = (float)(uint32_t)(r % (uint64_t)hp.pi_levels) * 0.125f;
+            ts.eval_pi[81 * (size_t)row + a] = v;
+        }
+    }
+    if (lane == 0) {
+        uint64_t r = mix64(h ^ 0xA5A5A5A5DEADBEEFull);
+        float v;
+        if (hp.v_levels == 0) v = (float)((int)(uint32_t)(r >> 40) - (1 << 23)) * 1.1920928955078125e-07f;  // 2^-23
+        else v = (float)((int)(r % (uint64_t)(2 * hp.v_levels + 1)) - hp.v_levels) * 0.25f;
+        ts.eval_v[row] = v;
+    }
+}
+
+__global__ void k_root_counts(TreeStore ts, uint32_t *__restrict__ counts, double *__restrict__ qout)
+{
+    int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (tree >= ts.E) return;
+    const TreeCtl *c = ts.ctl + tree;
+    int root = c->root_idx;
+    bool have = c->active && root >= 0;
+    Pos p;
+    uint32_t n = 0, off = 0;
+    uint32_t am[3] = {0, 0, 0};
+    if (have) {
+        const uint4 *hdr = ts.node_hdr + 2ull * ((size_t)tree * ts.capN + root);
+        unpack_hdr(hdr[0], hdr[1], p, n, off);
+        int status;
+        warp_legal_mask(p, lane, am, status);
+    }
+    EdgeBlock eb = edge_block(ts, tree, off, n);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int a = lane + 32 * q;
+        if (a < 81) {
+            uint32_t cnt = 0;
+            double qv = nan("");
+            if (have && ((am[q] >> lane) & 1u)) {
+                int j = edge_index(am, q, lane);
+                cnt = eb.N[j];
+                if (cnt) qv = eb.Q[j];
+            }
+            if (counts) counts[81 * (size_t)tree + a] = cnt;
+            if (qout) qout[81 * (size_t)tree + a] = qv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static inline int warp_grid(int n_warps, int threads) { return ceil_div(n_warps, threads / 32); }
+
+void launch_pack_fields(int n, const uint16_t *board, const uint16_t *occ, const int8_t *last, uint32_t *out,
+                        cudaStream_t st)
+{
+    k_pack_fields<<<ceil_div(n, 256), 256, 0, st>>>(n, board, occ, last, out);
+}
+
+void launch_reset(const TreeStore &ts, int env, cudaStream_t st)
+{
+    k_reset<<<env >= 0 ? 1 : ts.E, 256, 0, st>>>(ts, env);
+}
+
+void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uint8_t *active_dev, cudaStream_t st)
+{
+    k_set_roots<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, states_dev, active_dev);
+}
+
+void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st)
+{
+    k_select<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, cpuct);
+}
+
+void launch_expand_backup(const TreeStore &ts, cudaStream_t st)
+{
+    k_expand_backup<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts);
+}
+
+void launch_hash_eval(const TreeStore &ts, HashEvalParams hp, cudaStream_t st)
+{
+    k_hash_eval<<<warp_grid(ts.E, 256), 256, 0, st>>>(ts, hp);
+}
+
+void launch_root_counts(const TreeStore &ts, uint32_t *counts_dev, double *q_dev, cudaStream_t st)
+{
+    k_root_counts<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, counts_dev, q_dev);
+}
+
+}  // namespace tc

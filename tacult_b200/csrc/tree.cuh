@@ -1,0 +1,80 @@
+// Device-resident tree store and the warp-per-tree search kernels.
+//
+// Replaces the six per-env Python dicts of VectorizedMCTS
+// (/root/reference/src/tacult/base/mcts.py:152-162) and the per-level Python loops of
+// `_search` (mcts.py:243-342).  Semantics kept bit for bit:
+//   * a node exists once it has been expanded (`s in Ps`); nodes are found by full state key
+//     (board, occ, last_square — utac_game.py:222-241), so transpositions merge exactly as
+//     the reference's dict lookups do, and statistics persist across plies;
+//   * per edge: prior P (float64), mean value Q (float64, NOT a sum), visit count N;
+//     per node: Ns;
+//   * PUCT, expansion and backup use float64 with separately rounded operations
+//     (__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn: no FMA contraction).
+//
+// Layout in HBM (one warp owns one tree, so nothing below needs atomics):
+//   node header  32 B : mine[3] occ[3] meta(last_square+1 | n_edges<<8) edge_off   — immutable
+//   node Ns       4 B : separate array (the only mutable per-node word)
+//   edge block  24n B : P[n] f64 | Q[n] f64 | N[n] u32 | child[n] u32, edges in action order;
+//                       the action of edge j is the j-th set bit of the node's legal mask,
+//                       so it is recomputed from the header instead of stored
+//   hash table   4 B/slot, per tree, open addressing, entry = tag(12) | node index + 1 (20)
+#pragma once
+#include "common.cuh"
+#include "rules.cuh"
+
+namespace tc {
+
+constexpr uint32_t CHILD_UNRESOLVED = 0xFFFFFFFFu;
+constexpr uint32_t CHILD_TERM_BASE = 0xFFFFFFF0u;     // CHILD_TERM_BASE + status (1 lost, 2 draw, 3 won)
+constexpr int MAX_DEPTH = 82;
+constexpr uint32_t MAX_NODES_PER_TREE = (1u << 20) - 2;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+enum { LEAF_NONE = 0, LEAF_NN = 1, LEAF_TERMINAL = 2 };
+
+struct TreeCtl {
+    uint32_t root_state[8];
+    int32_t root_idx;        // -1: root position not (yet) in the tree
+    int32_t active;          // env passed a board, the position is not terminal and the pools are not exhausted
+    uint32_t n_nodes;
+    uint32_t n_edges;
+    int32_t leaf_kind;
+    int32_t leaf_node;
+    int32_t leaf_row;
+    int32_t path_len;
+    double leaf_value;       // value of a terminal leaf seen by its side to move (mcts.py:254-258)
+    // counters
+    unsigned long long sims, sum_depth, sum_legal, nn_leaves, sum_leaf_legal, terminal_leaves, transpositions;
+};
+
+struct TreeStore {
+    int E;
+    uint32_t capN, capE, hashSize;
+    uint4 *node_hdr;
+    uint32_t *node_Ns;
+    unsigned long long *edge_mem;
+    uint32_t *hash;
+    TreeCtl *ctl;
+    uint4 *path;
+    uint32_t *eval_state;    // [E][8]  leaves to evaluate, compacted
+    float *eval_pi;          // [E][81]
+    float *eval_v;           // [E]
+    int *eval_count;
+    int *error_flag;
+};
+
+struct HashEvalParams {
+    unsigned long long salt;
+    int pi_levels, v_levels;
+};
+
+void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uint8_t *active_dev, cudaStream_t st);
+void launch_reset(const TreeStore &ts, int env, cudaStream_t st);
+void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st);
+void launch_expand_backup(const TreeStore &ts, cudaStream_t st);
+void launch_hash_eval(const TreeStore &ts, HashEvalParams hp, cudaStream_t st);
+void launch_root_counts(const TreeStore &ts, uint32_t *counts_dev, double *q_dev, cudaStream_t st);
+void launch_pack_fields(int n, const uint16_t *board, const uint16_t *occ, const int8_t *last, uint32_t *out,
+                        cudaStream_t st);
+
+}  // namespace tc

@@ -1,0 +1,58 @@
+"""state_dict -> weight blob for tc_load_weights.
+
+Key names and shapes are the reference's own (`_UtacNNet`, /root/reference/src/tacult/network.py:44-79;
+listed in SURVEY.md §11.2), so `nnet.nnet.state_dict()` of a reference `NNetWrapper` can be passed in
+unchanged (torch tensors or numpy arrays).  BatchNorm folding happens inside the library.
+"""
+import numpy as np
+
+from ._lib import NetDesc
+
+
+def _np(x):
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def _strip(state_dict):
+    # torch.compile'd modules prefix keys with "_orig_mod."
+    out = {}
+    for k, v in state_dict.items():
+        out[k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k] = v
+    return out
+
+
+def state_dict_to_blob(state_dict):
+    sd = _strip(state_dict)
+    conv_in = _np(sd["conv_in.weight"])
+    channels, in_planes = conv_in.shape[0], conv_in.shape[1]
+    blocks = 0
+    while f"resnet.{blocks}.conv_block1.0.weight" in sd:
+        blocks += 1
+    emb = _np(sd["fc1.weight"]).shape[0]
+    if _np(sd["fc1.weight"]).shape[1] != 81 * channels:
+        raise ValueError("fc1.weight does not match 81 * channels inputs")
+    parts = []
+
+    def layer(prefix):
+        parts.append(_np(sd[prefix + ".weight"]).ravel())
+        parts.append(_np(sd[prefix + ".bias"]).ravel())
+
+    def bn(prefix):
+        for name in ("weight", "bias", "running_mean", "running_var"):
+            parts.append(_np(sd[f"{prefix}.{name}"]).ravel())
+
+    layer("conv_in")
+    bn("bn_in")
+    for k in range(blocks):
+        layer(f"resnet.{k}.conv_block1.0")
+        bn(f"resnet.{k}.conv_block1.1")
+        layer(f"resnet.{k}.conv_block2.0")
+        bn(f"resnet.{k}.conv_block2.1")
+    layer("fc1")
+    bn("fc_bn1")
+    layer("pi")
+    layer("v")
+    blob = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+    return NetDesc(int(channels), int(blocks), int(emb), int(in_planes)), blob
