@@ -136,6 +136,14 @@ int tc_root_counts(tc_engine *e, uint32_t *counts_host);
 int tc_root_q(tc_engine *e, double *q_host);
 int tc_get_stats(tc_engine *e, tc_stats *out);
 int tc_reset_stats(tc_engine *e);
+/* per-kernel-class device time, measured with CUDA events around every launch on the engine's stream
+ * (adds two event records per launch: enable only for profiling passes, not for headline timings) */
+enum {
+    TC_K_SELECT = 0, TC_K_EVAL_HASH = 1, TC_K_NN_STEM = 2, TC_K_NN_CONV = 3, TC_K_NN_FC1 = 4, TC_K_NN_HEADS = 5,
+    TC_K_EXPAND_BACKUP = 6, TC_K_OTHER = 7, TC_K_CLASSES = 8
+};
+int tc_profile_enable(tc_engine *e, int on);
+int tc_profile_read(tc_engine *e, double *ms_by_class, uint64_t *launches_by_class);   /* [TC_K_CLASSES]; resets */
 /* leaf evaluations recorded when cfg.eval_log_capacity > 0: returns how many, copies up to `max` */
 int tc_eval_log(tc_engine *e, int max, uint32_t *states_host, float *pi_host, float *v_host, int *count_out);
 
@@ -192,6 +200,7 @@ typedef struct {
     int32_t finished;                 /* 0 game in progress; 1 decisive: z = z_sign; 2 draw: z = z_sign * 1e-4 */
 } tc_example;
 int tc_selfplay_begin(tc_engine *e, const tc_selfplay_config *cfg);
+int tc_selfplay_configure(tc_engine *e, const tc_selfplay_config *cfg);   /* change sims/cpuct/... mid-run, no reset */
 int tc_selfplay_step(tc_engine *e, int plies);      /* plays `plies` lock-step plies; asynchronous on the stream */
 int tc_selfplay_sync(tc_engine *e);
 int tc_selfplay_get_stats(tc_engine *e, tc_selfplay_stats *out);

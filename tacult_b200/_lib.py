@@ -16,6 +16,7 @@ EVAL_NET_F32, EVAL_NET_BF16, EVAL_HASH = 0, 1, 2
 LIVE, LOST, DRAW, WON = 0, 1, 2, 3
 ACTIONS = 81
 STATE_WORDS = 8
+KERNEL_CLASSES = ("select", "eval_hash", "nn_stem", "nn_conv", "nn_fc1", "nn_heads", "expand_backup", "other")
 
 
 class TacultError(RuntimeError):
@@ -117,12 +118,15 @@ SYMBOLS = {
     "tc_get_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "tc_reset_stats": (_i, [_vp]),
     "tc_eval_log": (_i, [_vp, _i, _vp, _vp, _vp, _pi]),
+    "tc_profile_enable": (_i, [_vp, _i]),
+    "tc_profile_read": (_i, [_vp, _vp, _vp]),
     "tc_load_weights": (_i, [_vp, ctypes.POINTER(NetDesc), _vp, _sz]),
     "tc_weight_blob_floats": (_sz, [ctypes.POINTER(NetDesc)]),
     "tc_forward": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "tc_forward_states": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "tc_forward_states_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "tc_selfplay_begin": (_i, [_vp, ctypes.POINTER(SelfPlayConfig)]),
+    "tc_selfplay_configure": (_i, [_vp, ctypes.POINTER(SelfPlayConfig)]),
     "tc_selfplay_step": (_i, [_vp, _i]),
     "tc_selfplay_sync": (_i, [_vp]),
     "tc_selfplay_get_stats": (_i, [_vp, ctypes.POINTER(SelfPlayStats)]),

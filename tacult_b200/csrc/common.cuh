@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/tacult_b200.h"
 
@@ -68,5 +69,54 @@ struct DevBuf {                     // RAII device allocation
 };
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (tc_profile_*).
+struct Profiler {
+    bool on = false;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t open_a = nullptr;
+    int open_cls = -1;
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int cls, cudaStream_t st)
+    {
+        if (!on) return;
+        open_a = get();
+        open_cls = cls;
+        cudaEventRecord(open_a, st);
+    }
+    void end(cudaStream_t st)
+    {
+        if (!on || open_cls < 0) return;
+        cudaEvent_t b = get();
+        cudaEventRecord(b, st);
+        spans.push_back({open_cls, open_a, b});
+        open_cls = -1;
+    }
+    // sums elapsed ms / launches per class and recycles the events; call after a stream synchronise
+    void collect(double *ms, unsigned long long *launches, int n_cls)
+    {
+        for (auto &s : spans) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, s.a, s.b);
+            if (s.cls < n_cls) { ms[s.cls] += t; launches[s.cls] += 1; }
+            pool.push_back(s.a);
+            pool.push_back(s.b);
+        }
+        spans.clear();
+    }
+    ~Profiler()
+    {
+        for (auto &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
 
 }  // namespace tc

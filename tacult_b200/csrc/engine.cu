@@ -106,6 +106,7 @@ struct tc_engine {
     DevBuf<int> sp_finished_count;
     DevBuf<unsigned long long> sp_stats;
     unsigned long long launches = 0;
+    Profiler prof;
 };
 
 static int check_engine(tc_engine *e)
@@ -316,17 +317,21 @@ extern "C" int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, co
 static int enqueue_simulation(tc_engine *e, double cpuct)
 {
     TC_CUDA(cudaMemsetAsync(e->eval_count.p, 0, sizeof(int), e->stream));
+    e->prof.begin(TC_K_SELECT, e->stream);
     launch_select(e->ts, cpuct, e->stream);
+    e->prof.end(e->stream);
     e->launches += 1;
     if (e->evaluator == TC_EVAL_HASH) {
+        e->prof.begin(TC_K_EVAL_HASH, e->stream);
         launch_hash_eval(e->ts, e->hash_params, e->stream);
+        e->prof.end(e->stream);
         e->launches += 1;
     } else if (e->evaluator == TC_EVAL_NET_F32) {
         e->launches += e->net32.forward(e->ts.E, e->eval_count.p, e->eval_state.p, nullptr, e->eval_pi.p, e->eval_v.p,
-                                        nullptr, e->stream);
+                                        nullptr, e->stream, &e->prof);
     } else {
         int n = e->net16.forward(e->ts.E, e->eval_count.p, e->eval_state.p, nullptr, e->eval_pi.p, e->eval_v.p,
-                                 nullptr, e->stream);
+                                 nullptr, e->stream, &e->prof);
         if (n < 0) return n;
         e->launches += n;
     }
@@ -336,8 +341,33 @@ static int enqueue_simulation(tc_engine *e, double cpuct)
         k_log_advance<<<1, 1, 0, e->stream>>>(e->ts, e->log_count.p);
         e->launches += 2;
     }
+    e->prof.begin(TC_K_EXPAND_BACKUP, e->stream);
     launch_expand_backup(e->ts, e->stream);
+    e->prof.end(e->stream);
     e->launches += 1;
+    return TC_OK;
+}
+
+extern "C" int tc_profile_enable(tc_engine *e, int on)
+{
+    TC_TRY(check_engine(e));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    double ms[TC_K_CLASSES] = {0};
+    unsigned long long n[TC_K_CLASSES] = {0};
+    e->prof.collect(ms, n, TC_K_CLASSES);
+    e->prof.on = on != 0;
+    return TC_OK;
+}
+
+extern "C" int tc_profile_read(tc_engine *e, double *ms_by_class, uint64_t *launches_by_class)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(ms_by_class && launches_by_class, TC_EINVAL, "tc_profile_read: null output");
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    unsigned long long n[TC_K_CLASSES] = {0};
+    for (int k = 0; k < TC_K_CLASSES; ++k) ms_by_class[k] = 0.0;
+    e->prof.collect(ms_by_class, n, TC_K_CLASSES);
+    for (int k = 0; k < TC_K_CLASSES; ++k) launches_by_class[k] = n[k];
     return TC_OK;
 }
 
@@ -567,22 +597,35 @@ extern "C" int tc_selfplay_begin(tc_engine *e, const tc_selfplay_config *cfg)
     return TC_OK;
 }
 
+extern "C" int tc_selfplay_configure(tc_engine *e, const tc_selfplay_config *cfg)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(e->sp_ready, TC_ESTATE, "tc_selfplay_configure before tc_selfplay_begin");
+    TC_CHECK(cfg && cfg->num_sims >= 1 && cfg->temp_threshold >= 0, TC_EINVAL, "tc_selfplay_configure: bad config");
+    e->sp_cfg = *cfg;
+    return TC_OK;
+}
+
 extern "C" int tc_selfplay_step(tc_engine *e, int plies)
 {
     TC_TRY(check_engine(e));
     TC_CHECK(e->sp_ready, TC_ESTATE, "tc_selfplay_step before tc_selfplay_begin");
     TC_CHECK(plies >= 0, TC_EINVAL, "negative plies");
     for (int p = 0; p < plies; ++p) {
+        e->prof.begin(TC_K_OTHER, e->stream);
         launch_selfplay_roots(e->sp, e->stream);
         launch_set_roots(e->ts, e->root_states.p, e->root_active.p, e->stream);
+        e->prof.end(e->stream);
         e->launches += 2;
         for (int s = 0; s < e->sp_cfg.num_sims; ++s) TC_TRY(enqueue_simulation(e, e->sp_cfg.cpuct));
+        e->prof.begin(TC_K_OTHER, e->stream);
         launch_selfplay_move(e->ts, e->sp, e->sp_cfg, e->stream);
         e->launches += 1;
         if (e->sp_cfg.auto_reset) {
             launch_reset_marked(e->ts, e->sp, e->stream);
             e->launches += 1;
         }
+        e->prof.end(e->stream);
     }
     TC_CUDA(cudaGetLastError());
     return TC_OK;

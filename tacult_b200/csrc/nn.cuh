@@ -32,7 +32,7 @@ struct NetF32 {
     // input: packed states (states != null) or dense planes (obs != null); count_dev (optional) holds the
     // live batch size on the device, `batch` is the launch bound.  Returns the number of kernels launched.
     int forward(int batch, const int *count_dev, const uint32_t *states, const float *obs, float *pi, float *v,
-                float *logits, cudaStream_t st);
+                float *logits, cudaStream_t st, Profiler *prof = nullptr);
 };
 
 size_t blob_floats(const tc_net_desc &d);

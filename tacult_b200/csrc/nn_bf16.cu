@@ -14,7 +14,8 @@ int NetBF16::upload(const FoldedNet &, int)
     return TC_OK;
 }
 
-int NetBF16::forward(int, const int *, const uint32_t *, const float *, float *, float *, float *, cudaStream_t)
+int NetBF16::forward(int, const int *, const uint32_t *, const float *, float *, float *, float *, cudaStream_t,
+                     Profiler *)
 {
     set_error("bf16 evaluator: %s", why_not.c_str());
     return TC_ESTATE;

@@ -21,7 +21,7 @@ struct NetBF16 {
     int upload(const FoldedNet &f, int capacity);
     // same contract as NetF32::forward; returns the number of kernels launched or a negative TC_E* code
     int forward(int batch, const int *count_dev, const uint32_t *states, const float *obs, float *pi, float *v,
-                float *logits, cudaStream_t st);
+                float *logits, cudaStream_t st, Profiler *prof = nullptr);
 };
 
 }  // namespace tc

@@ -400,31 +400,43 @@ int NetF32::upload(const FoldedNet &f, int cap)
 }
 
 int NetF32::forward(int batch, const int *count_dev, const uint32_t *states, const float *obs, float *pi, float *v,
-                    float *logits, cudaStream_t st)
+                    float *logits, cudaStream_t st, Profiler *prof)
 {
+    Profiler none;
+    if (!prof) prof = &none;
     const int C = d.channels, E = d.embedding_size, I = d.in_planes;
     int launches = 0;
+    prof->begin(TC_K_NN_STEM, st);
     k_stem_f32<<<batch, 256, sizeof(float) * I * 121, st>>>(batch, count_dev, states, obs, I, C, stem_w.p, stem_b.p,
                                                             act[0].p);
+    prof->end(st);
     ++launches;
     const int CK = C < 32 ? C : 32, CT = CK;
     dim3 cgrid(ceil_div(batch, CONV_G), C / CT);
     const size_t csm = conv_smem_bytes(C);
     float *x = act[0].p, *y = act[1].p, *z = act[2].p;
     for (int b = 0; b < d.num_residual_blocks; ++b) {
+        prof->begin(TC_K_NN_CONV, st);
         k_conv3x3_f32<<<cgrid, CONV_THREADS, csm, st>>>(batch, count_dev, C, CK, CT, x, conv_w[2 * b].p,
                                                         conv_b[2 * b].p, nullptr, y);
+        prof->end(st);
+        prof->begin(TC_K_NN_CONV, st);
         k_conv3x3_f32<<<cgrid, CONV_THREADS, csm, st>>>(batch, count_dev, C, CK, CT, y, conv_w[2 * b + 1].p,
                                                         conv_b[2 * b + 1].p, x, z);
+        prof->end(st);
         launches += 2;
         float *tmp = x;
         x = z;
         z = tmp;
     }
     dim3 lgrid(ceil_div(batch, 64), ceil_div(E, 64));
+    prof->begin(TC_K_NN_FC1, st);
     k_linear_relu_f32<<<lgrid, 256, 0, st>>>(batch, count_dev, 81 * C, E, x, fc1_w.p, fc1_b.p, emb.p);
+    prof->end(st);
+    prof->begin(TC_K_NN_HEADS, st);
     k_heads_f32<<<ceil_div(batch, 8), 256, sizeof(float) * 8 * E, st>>>(batch, count_dev, E, emb.p, head_w.p,
                                                                         head_b.p, pi, v, logits);
+    prof->end(st);
     launches += 2;
     return launches;
 }

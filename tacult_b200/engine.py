@@ -138,6 +138,16 @@ class Engine:
     def reset_stats(self):
         check(self.lib.tc_reset_stats(self.handle))
 
+    def profile_enable(self, on=True):
+        check(self.lib.tc_profile_enable(self.handle, int(bool(on))))
+
+    def profile_read(self):
+        """{kernel class: (total device ms, launches)} since the last read."""
+        ms = np.zeros(len(_lib.KERNEL_CLASSES), dtype=np.float64)
+        n = np.zeros(len(_lib.KERNEL_CLASSES), dtype=np.uint64)
+        check(self.lib.tc_profile_read(self.handle, ptr(ms), ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
     def eval_log(self, max_rows):
         states = np.empty((max_rows, 8), dtype=np.uint32)
         pi = np.empty((max_rows, 81), dtype=np.float32)
@@ -152,6 +162,11 @@ class Engine:
         cfg = _lib.SelfPlayConfig(int(num_sims), int(temp_threshold), int(bool(auto_reset)), 0, float(cpuct),
                                   int(seed) & (2 ** 64 - 1))
         check(self.lib.tc_selfplay_begin(self.handle, ctypes.byref(cfg)))
+
+    def selfplay_configure(self, num_sims, cpuct, temp_threshold, seed=0, auto_reset=False):
+        cfg = _lib.SelfPlayConfig(int(num_sims), int(temp_threshold), int(bool(auto_reset)), 0, float(cpuct),
+                                  int(seed) & (2 ** 64 - 1))
+        check(self.lib.tc_selfplay_configure(self.handle, ctypes.byref(cfg)))
 
     def selfplay_step(self, plies=1):
         check(self.lib.tc_selfplay_step(self.handle, int(plies)))

@@ -56,3 +56,42 @@ def state_dict_to_blob(state_dict):
     layer("v")
     blob = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
     return NetDesc(int(channels), int(blocks), int(emb), int(in_planes)), blob
+
+
+def random_state_dict(seed, channels=32, num_residual_blocks=3, embedding_size=256, in_planes=4):
+    """Random-init weights with the reference's state_dict layout (synthetic benchmark input;
+    He-scaled convolutions, non-trivial BatchNorm statistics so that folding is exercised)."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+
+    def conv(prefix, cin, cout):
+        sd[prefix + ".weight"] = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float32)
+        sd[prefix + ".bias"] = (rng.standard_normal(cout) * 0.05).astype(np.float32)
+
+    def bn(prefix, n):
+        sd[prefix + ".weight"] = rng.uniform(0.6, 1.4, n).astype(np.float32)
+        sd[prefix + ".bias"] = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        sd[prefix + ".running_mean"] = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        sd[prefix + ".running_var"] = rng.uniform(0.5, 1.5, n).astype(np.float32)
+
+    def linear(prefix, fin, fout, gain):
+        sd[prefix + ".weight"] = (rng.standard_normal((fout, fin)) * gain / np.sqrt(fin)).astype(np.float32)
+        sd[prefix + ".bias"] = (rng.standard_normal(fout) * 0.05).astype(np.float32)
+
+    conv("conv_in", in_planes, channels)
+    bn("bn_in", channels)
+    for k in range(num_residual_blocks):
+        conv(f"resnet.{k}.conv_block1.0", channels, channels)
+        bn(f"resnet.{k}.conv_block1.1", channels)
+        conv(f"resnet.{k}.conv_block2.0", channels, channels)
+        bn(f"resnet.{k}.conv_block2.1", channels)
+    linear("fc1", 81 * channels, embedding_size, np.sqrt(2.0))
+    bn("fc_bn1", embedding_size)
+    linear("pi", embedding_size, 81, 2.0)
+    linear("v", embedding_size, 1, 1.0)
+    return sd
+
+
+def flops_per_eval(channels, blocks, emb, in_planes=4):
+    """Algorithmic FLOPs of one leaf evaluation."""
+    return 2 * 81 * 9 * channels * (in_planes + 2 * blocks * channels) + 2 * 81 * channels * emb + 2 * emb * 82

@@ -1,0 +1,188 @@
+"""CUDA search engine vs the reference: root visit counts must be IDENTICAL when both sides see identical
+evaluator outputs (BASELINE.json north_star).  Three anchors:
+  1. golden counts recorded from the live reference VectorizedMCTS (tests/golden/mcts_*.npz);
+  2. the oracle restatement run here on fresh seeds (also compares every root Q bit for bit);
+  3. record/replay: the GPU engine's own fp32-network leaf evaluations replayed through the oracle search."""
+import logging
+
+import numpy as np
+import pytest
+
+import resnet_oracle
+import tacult_b200 as tb
+from evaluators import HashEvaluator, ReplayEvaluator
+from game_oracle import OracleGame
+from mcts_oracle import OracleVectorizedMCTS
+from utac_gym.core import GameState
+
+pytestmark = pytest.mark.gpu
+logging.disable(logging.ERROR)
+
+
+class HashNet:
+    """Tells tacult_b200.VectorizedMCTS to use the device-side hash evaluator (same spec as HashEvaluator)."""
+    def __init__(self, salt, pi_levels=0, v_levels=0):
+        self.tc_hash_params = (salt, pi_levels, v_levels)
+
+
+@pytest.mark.parametrize("name", ["mcts_selfplay_a.npz", "mcts_selfplay_ties.npz", "mcts_selfplay_c1.npz"])
+def test_selfplay_counts_match_reference_golden(golden, make_args, name):
+    g = golden(name)
+    args = make_args(numEnvs=int(g["envs"]), numMCTSSims=int(g["sims"]), cpuct=float(g["cpuct"]))
+    mcts = tb.VectorizedMCTS(OracleGame(), HashNet(int(g["salt"]), int(g["pi_levels"]), int(g["v_levels"])), args)
+    for ply in range(len(g["roots"])):
+        boards = [GameState.from_packed(w) for w in g["roots"][ply]]
+        counts = mcts.rootCounts(boards)
+        assert (counts == g["counts"][ply]).all(), f"{name} ply {ply}"
+    st = mcts.engine.stats()
+    assert st["sims"] == int(g["alive"].sum()) * int(g["sims"])
+
+
+@pytest.mark.parametrize("name", ["mcts_arena_2sims.npz", "mcts_arena_16sims.npz"])
+def test_arena_counts_match_reference_golden(golden, make_args, name):
+    g = golden(name)
+    args = make_args(numEnvs=int(g["envs"]), numMCTSSims=int(g["sims"]), cpuct=float(g["cpuct"]))
+    engines = [tb.VectorizedMCTS(OracleGame(), HashNet(int(s)), args) for s in g["salts"]]
+    for ply in range(len(g["roots"])):
+        boards = [GameState.from_packed(w) for w in g["roots"][ply]]
+        counts = engines[int(g["movers"][ply])].rootCounts(boards)
+        assert (counts == g["counts"][ply]).all(), f"{name} ply {ply}"
+
+
+def play_both(make_args, envs, sims, cpuct, salt, pi_levels, v_levels, seed, max_plies=200):
+    """GPU engine and oracle search side by side on a fresh self-play; counts and root Q compared every ply."""
+    args = make_args(numEnvs=envs, numMCTSSims=sims, cpuct=cpuct)
+    game = OracleGame()
+    gpu = tb.VectorizedMCTS(game, HashNet(salt, pi_levels, v_levels), args)
+    cpu = OracleVectorizedMCTS(game, HashEvaluator(salt, pi_levels, v_levels), args)
+    boards = [game.getInitBoard() for _ in range(envs)]
+    players = np.ones(envs, dtype=int)
+    rng = np.random.RandomState(seed)
+    plies = 0
+    while plies < max_plies:
+        alive = [game.getGameEnded(boards[i], players[i]) == 0 for i in range(envs)]
+        if not any(alive):
+            break
+        canon = [game.getCanonicalForm(boards[i], players[i]) for i in range(envs)]
+        got = gpu.rootCounts(canon)
+        for _ in range(sims):
+            cpu.search(canon)
+        want = cpu.root_counts(canon)
+        assert (got == want).all(), f"ply {plies}"
+        q = gpu.engine.root_q()
+        for i in range(envs):
+            key = game.stringRepresentation(canon[i])
+            for a in range(81):
+                ref_q = cpu.Qsa[i].get((key, a))
+                if ref_q is None:
+                    assert np.isnan(q[i, a])
+                else:
+                    assert q[i, a] == ref_q, (plies, i, a)      # float64, bit for bit
+        for i in range(envs):
+            if alive[i]:
+                p = want[i].astype(float)
+                boards[i], players[i] = game.getNextState(boards[i], int(players[i]), int(rng.choice(81, p=p / p.sum())))
+        plies += 1
+    return gpu, cpu
+
+
+def test_counts_and_q_match_oracle_fresh_seeds(make_args):
+    gpu, cpu = play_both(make_args, envs=5, sims=48, cpuct=2.4, salt=1234, pi_levels=0, v_levels=0, seed=1)
+    st = gpu.engine.stats()
+    assert st["sims"] == cpu.stat_sims - 0 or st["sims"] <= cpu.stat_sims     # oracle also counts sims on finished roots
+    assert st["nn_leaves"] == cpu.stat_leaf_evals
+    assert st["sum_depth"] == cpu.stat_sum_depth
+    assert st["nodes_in_use"] == sum(len(x) for x in cpu.Ps)
+
+
+def test_counts_match_oracle_with_ties_zero_priors_and_draw_values(make_args):
+    play_both(make_args, envs=4, sims=32, cpuct=1.25, salt=77, pi_levels=2, v_levels=1, seed=2)
+
+
+def test_deep_search_transpositions(make_args):
+    # many simulations from few positions: transpositions and deep paths (> 32 levels late in the game)
+    gpu, cpu = play_both(make_args, envs=2, sims=400, cpuct=0.5, salt=5, pi_levels=0, v_levels=0, seed=3, max_plies=12)
+    assert gpu.engine.stats()["transpositions"] > 0
+
+
+def test_none_and_terminal_roots(make_args, golden):
+    args = make_args(numEnvs=4, numMCTSSims=10, cpuct=2.4)
+    mcts = tb.VectorizedMCTS(OracleGame(), HashNet(3), args)
+    fin = GameState.from_packed(golden("rules_playouts.npz")["final_state"][0])
+    assert fin.is_terminal()
+    counts = mcts.rootCounts([GameState(), None, fin, GameState()])
+    assert counts[0].sum() == 9 and counts[3].sum() == 9 and counts[1].sum() == 0 and counts[2].sum() == 0
+    np.random.seed(0)
+    probs = mcts.getActionProbs([GameState(), None, fin, GameState()], temps=np.array([1, 1, 0, 0]))
+    assert abs(probs[0].sum() - 1) < 1e-12 and np.isnan(probs[1]).all() and probs[2].sum() == 1 and probs[3].max() == 1
+
+
+def test_reset_and_capacity_error(make_args):
+    args = make_args(numEnvs=2, numMCTSSims=20, cpuct=2.4, tc_max_nodes_per_tree=8)
+    mcts = tb.VectorizedMCTS(OracleGame(), HashNet(3), args)
+    with pytest.raises(tb._lib.TacultError) as err:
+        mcts.rootCounts([GameState(), GameState()])
+    assert err.value.code == tb._lib.TC_ECAPACITY
+    args = make_args(numEnvs=2, numMCTSSims=20, cpuct=2.4)
+    mcts = tb.VectorizedMCTS(OracleGame(), HashNet(3), args)
+    first = mcts.rootCounts([GameState(), GameState()])
+    again = mcts.rootCounts([GameState(), GameState()])
+    assert again.sum() == first.sum() + 40            # statistics persist (coach.py:162,175-176)
+    mcts.reset(0)
+    third = mcts.rootCounts([GameState(), GameState()])
+    assert (third[0] == first[0]).all() and third[1].sum() == again[1].sum() + 20
+
+
+def test_full_size_properties():
+    """C3-sized engine (4096 trees): size-independent invariants of one search call."""
+    eng = tb.Engine(4096, 200 * 4 + 64, hash_salt=9)
+    eng.set_roots_packed(np.zeros((4096, 8), dtype=np.uint32))
+    eng.search(200, 2.4)
+    counts = eng.root_counts()
+    assert (counts.sum(1) == 199).all()               # the first simulation expands the root
+    assert (counts == counts[0]).all()                # identical positions + identical evaluator => identical trees
+    st = eng.stats()
+    assert st["sims"] == 4096 * 200 and st["nn_leaves"] + st["terminal_leaves"] == st["sims"]
+    assert st["max_nodes_one_tree"] <= 200
+
+
+def test_record_replay_with_network_evaluator(make_args):
+    """Identical evaluator outputs, real network: the engine logs every leaf (state, pi, v) its fp32 ResNet
+    produced; the oracle search replays those exact float32 values and must reach the same visit counts."""
+    envs, sims = 6, 40
+    sd = resnet_oracle.make_state_dict(11, channels=16, num_residual_blocks=2, embedding_size=64)
+
+    class Net:                     # the shape tacult_b200.VectorizedMCTS expects: .nnet.state_dict()
+        class nnet:
+            @staticmethod
+            def state_dict():
+                return sd
+    args = make_args(numEnvs=envs, numMCTSSims=sims, cpuct=2.4, tc_eval_log_capacity=envs * sims * 20, tc_evaluator="f32")
+    game = OracleGame()
+    gpu = tb.VectorizedMCTS(game, Net(), args)
+    boards = [game.getInitBoard() for _ in range(envs)]
+    players = np.ones(envs, dtype=int)
+    rng = np.random.RandomState(4)
+    history = []
+    for ply in range(16):
+        canon = [game.getCanonicalForm(boards[i], players[i]) for i in range(envs)]
+        counts = gpu.rootCounts(canon)
+        history.append((canon, counts))
+        for i in range(envs):
+            p = counts[i].astype(float)
+            boards[i], players[i] = game.getNextState(boards[i], int(players[i]), int(rng.choice(81, p=p / p.sum())))
+    states, pi, v, total = gpu.engine.eval_log(envs * sims * 20)
+    assert total == len(states) > 0
+    table = {}
+    for k in range(len(states)):
+        obs = np.asarray(GameState.from_packed(states[k]).get_obs())
+        table[ReplayEvaluator.key_of(obs)] = (pi[k], v[k])
+    cpu = OracleVectorizedMCTS(game, ReplayEvaluator(table), make_args(numEnvs=envs, numMCTSSims=sims, cpuct=2.4))
+    for canon, counts in history:
+        for _ in range(sims):
+            cpu.search(canon)
+        assert (cpu.root_counts(canon) == counts).all()
+    # and the logged evaluations themselves are the reference network's, to fp32 tolerance
+    obs = np.stack([np.asarray(GameState.from_packed(s).get_obs()).reshape(4, 9, 9) for s in states[:256]])
+    rpi, rv = resnet_oracle.forward(sd, obs)
+    assert np.abs(rpi.numpy() - pi[:256]).max() < 1e-3 and np.abs(rv.numpy().ravel() - v[:256]).max() < 1e-3

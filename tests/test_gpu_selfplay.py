@@ -1,0 +1,77 @@
+"""Device-resident self-play driver vs Coach.executeEpisode semantics
+(/root/reference/src/tacult/base/coach.py:96-157), checked with the oracle rules and search."""
+import logging
+
+import numpy as np
+import pytest
+
+import tacult_b200 as tb
+from evaluators import HashEvaluator
+from game_oracle import OracleGame
+from mcts_oracle import OracleVectorizedMCTS
+from utac_gym.core import GameState
+
+pytestmark = pytest.mark.gpu
+logging.disable(logging.ERROR)
+
+
+def run_games(envs, sims, threshold, seed, salt):
+    eng = tb.Engine(envs, sims * 82 + 64, hash_salt=salt)
+    eng.selfplay_begin(sims, 2.4, threshold, seed=seed, auto_reset=False)
+    for _ in range(81):
+        eng.selfplay_step(1)
+        if eng.selfplay_stats()["games_finished"] == envs:
+            break
+    eng.selfplay_sync()
+    return eng, eng.selfplay_drain()
+
+
+def test_trajectories_follow_the_rules_and_the_search():
+    envs, sims, threshold, salt = 6, 24, 6, 31
+    eng, recs = run_games(envs, sims, threshold, seed=5, salt=salt)
+    stats = eng.selfplay_stats()
+    assert stats["games_finished"] == envs and stats["examples"] == 0 and len(recs) == stats["plies"]
+    assert stats["sims"] == stats["plies"] * sims
+    assert stats["first_player_wins"] + stats["second_player_wins"] + stats["draws"] == envs
+    game = OracleGame()
+    args = type("A", (dict,), {"__getattr__": dict.__getitem__})(numEnvs=envs, numMCTSSims=sims, cpuct=2.4)
+    cpu = OracleVectorizedMCTS(game, HashEvaluator(salt), args)
+    by_env = {e: sorted([r for r in recs if r["env"] == e], key=lambda r: r["ply"]) for e in range(envs)}
+    max_len = max(len(v) for v in by_env.values())
+    boards = [GameState() for _ in range(envs)]
+    players = [1] * envs
+    for ply in range(max_len):
+        canon = [game.getCanonicalForm(boards[e], players[e]) if ply < len(by_env[e]) else None for e in range(envs)]
+        for _ in range(sims):
+            cpu.search(canon)
+        for e in range(envs):
+            if ply >= len(by_env[e]):
+                continue
+            r = by_env[e][ply]
+            assert (r["state"] == canon[e].packed()).all() and r["player"] == players[e] and r["ply"] == ply
+            want = cpu.root_counts([c if c is not None else GameState() for c in canon])[e]
+            assert (r["counts"] == want).all()                       # same visit counts as the CPU search
+            assert r["tau_one"] == (1 if ply + 1 < threshold else 0)  # coach.py:124-125
+            a = int(r["action"])
+            assert want[a] > 0 and (r["tau_one"] or want[a] == want.max())
+            boards[e], players[e] = game.getNextState(boards[e], players[e], a)
+    for e in range(envs):
+        result = game.getGameEnded(boards[e], players[e])             # coach.py:143
+        assert result != 0
+        for r in by_env[e]:
+            z = result * ((-1) ** (int(r["player"]) != players[e]))   # coach.py:149
+            got = float(r["z_sign"]) * (1e-4 if r["finished"] == 2 else 1.0)
+            assert got == pytest.approx(z) and r["finished"] in (1, 2)
+
+
+def test_auto_reset_keeps_all_envs_busy():
+    envs, sims = 64, 8
+    eng = tb.Engine(envs, sims * 82 + 64, hash_salt=2)
+    eng.selfplay_begin(sims, 2.4, 10, seed=1, auto_reset=True)
+    eng.selfplay_step(150)
+    eng.selfplay_sync()
+    st = eng.selfplay_stats()
+    assert st["plies"] == envs * 150 and st["games_finished"] >= envs
+    recs = eng.selfplay_drain()
+    assert len(recs) > 0 and (recs["finished"] > 0).all()
+    assert set(np.unique(recs["game"])) >= {0, 1}
