@@ -234,9 +234,9 @@ def run_b200(a):
 
     # ---- device-resident self-play: the headline `value` --------------------------------------
     seed = 1000 + rank
-    eng.selfplay_begin(2, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True)
+    eng.selfplay_begin(2, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True, discard_records=True)
     eng.selfplay_step(a.stagger_plies)                       # spread the envs over all game phases
-    eng.selfplay_configure(sims, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True)
+    eng.selfplay_configure(sims, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True)   # records kept from here on
     eng.selfplay_step(a.warmup)
     eng.selfplay_sync()
     eng.selfplay_drain()

@@ -170,12 +170,13 @@ int tc_forward_states_dev(tc_engine *e, int evaluator, int batch, const uint32_t
 
 /* ---- device-resident self-play driver: Coach.executeEpisode semantics
  *      (/root/reference/src/tacult/base/coach.py:87-157) without host round trips ------------------------- */
+#define TC_SP_DISCARD_RECORDS 1
 typedef struct {
     int32_t num_sims;            /* args.numMCTSSims */
     int32_t temp_threshold;      /* args.tempThreshold: tau=1 while episodeStep < threshold (coach.py:124-125) */
     int32_t auto_reset;          /* 1: a finished env restarts a new game with a fresh tree (the reference's
                                     commented-out block coach.py:114-122); 0: it idles like the reference */
-    int32_t reserved;
+    int32_t flags;               /* TC_SP_DISCARD_RECORDS: play, but keep no trajectory records (warm-up, benchmarks) */
     double cpuct;
     uint64_t seed;
 } tc_selfplay_config;

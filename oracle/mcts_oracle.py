@@ -50,6 +50,7 @@ class OracleVectorizedMCTS:
         self.stat_terminal_leaves = 0
         self.stat_sum_depth = 0
         self.stat_sims = 0
+        self.stat_transpositions = 0
 
     def reset(self, i):  # mcts.py:165-172
         for table in (self.Qsa, self.Nsa, self.Ns, self.Ps, self.Es, self.Vs):
@@ -156,6 +157,8 @@ class OracleVectorizedMCTS:
                         best_u, best_a = u, a
                 child, child_player = game.getNextState(boards[i], 1, best_a)
                 nxt[i] = game.getCanonicalForm(child, child_player)
+                if (s, best_a) not in q_of and game.stringRepresentation(nxt[i]) in self.Ps[i]:
+                    self.stat_transpositions += 1      # instrumentation only: first use of an edge into a known node
                 step.append((i, s, best_a))
             levels.append(step)
             boards = nxt

@@ -71,7 +71,7 @@ class SelfPlayConfig(ctypes.Structure):
         ("num_sims", ctypes.c_int32),
         ("temp_threshold", ctypes.c_int32),
         ("auto_reset", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
         ("cpuct", ctypes.c_double),
         ("seed", ctypes.c_uint64),
     ]

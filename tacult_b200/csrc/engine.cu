@@ -575,14 +575,14 @@ extern "C" int tc_selfplay_begin(tc_engine *e, const tc_selfplay_config *cfg)
     if (!e->sp_ready) {
         TC_CUDA(e->sp_env.alloc(E));
         TC_CUDA(e->sp_pending.alloc(E * 81));
-        TC_CUDA(e->sp_finished.alloc(E * 96));
+        TC_CUDA(e->sp_finished.alloc(E * 256));
         TC_CUDA(e->sp_finished_count.alloc(1));
         TC_CUDA(e->sp_stats.alloc(8));
         e->sp.E = (int)E;
         e->sp.env = e->sp_env.p;
         e->sp.pending = e->sp_pending.p;
         e->sp.finished = e->sp_finished.p;
-        e->sp.finished_cap = (int)(E * 96);
+        e->sp.finished_cap = (int)(E * 256);
         e->sp.finished_count = e->sp_finished_count.p;
         e->sp.stats = e->sp_stats.p;
         e->sp.root_states = e->root_states.p;
@@ -661,8 +661,13 @@ static int drain_common(tc_engine *e, int max, tc_example *out, bool to_host, in
     TC_CUDA(cudaMemcpyAsync(&nfin, e->sp_finished_count.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     TC_CUDA(cudaMemcpyAsync(&dropped, e->sp_stats.p + 6, sizeof dropped, cudaMemcpyDeviceToHost, e->stream));
     TC_CUDA(cudaStreamSynchronize(e->stream));
-    TC_CHECK(dropped == 0, TC_ECAPACITY, "self-play record buffer overflowed: %llu records dropped; drain more often",
-             dropped);
+    if (dropped != 0) {      // fail loudly, then start over with an empty buffer
+        cudaMemsetAsync(e->sp_finished_count.p, 0, sizeof(int), e->stream);
+        cudaMemsetAsync(e->sp_stats.p + 6, 0, sizeof(unsigned long long), e->stream);
+        cudaStreamSynchronize(e->stream);
+        TC_CHECK(false, TC_ECAPACITY, "self-play record buffer (%d records) overflowed: %llu records dropped, the "
+                 "buffer was discarded; call tc_selfplay_drain more often", e->sp.finished_cap, dropped);
+    }
     TC_CHECK(nfin <= max, TC_EINVAL, "tc_selfplay_drain: %d records pending, buffer holds %d", nfin, max);
     if (nfin > 0)
         TC_CUDA(cudaMemcpyAsync(out, e->sp_finished.p, (size_t)nfin * sizeof(tc_example),

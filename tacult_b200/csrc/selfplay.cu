@@ -161,9 +161,12 @@ __global__ void __launch_bounds__(128) k_selfplay_move(TreeStore ts, SelfPlaySto
         }
         __syncwarp();
         int base = 0;
-        if (lane == 0) base = atomicAdd(sp.finished_count, n_rec);
+        const bool keep = !(cfg.flags & TC_SP_DISCARD_RECORDS);
+        if (keep && lane == 0) base = atomicAdd(sp.finished_count, n_rec);
         base = __shfl_sync(FULL, base, 0);
-        if (base + n_rec <= sp.finished_cap) {
+        if (!keep) {
+            // records are not wanted (warm-up / throughput runs)
+        } else if (base + n_rec <= sp.finished_cap) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(game_recs);
             uint32_t *dst = reinterpret_cast<uint32_t *>(sp.finished + base);
             const int words = n_rec * (int)(sizeof(tc_example) / 4);

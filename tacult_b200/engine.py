@@ -158,13 +158,15 @@ class Engine:
         return states[:k], pi[:k], v[:k], n.value
 
     # -- device-resident self-play -------------------------------------------------------------
-    def selfplay_begin(self, num_sims, cpuct, temp_threshold, seed=0, auto_reset=False):
-        cfg = _lib.SelfPlayConfig(int(num_sims), int(temp_threshold), int(bool(auto_reset)), 0, float(cpuct),
+    def selfplay_begin(self, num_sims, cpuct, temp_threshold, seed=0, auto_reset=False, discard_records=False):
+        cfg = _lib.SelfPlayConfig(int(num_sims), int(temp_threshold), int(bool(auto_reset)), int(bool(discard_records)),
+                                  float(cpuct),
                                   int(seed) & (2 ** 64 - 1))
         check(self.lib.tc_selfplay_begin(self.handle, ctypes.byref(cfg)))
 
-    def selfplay_configure(self, num_sims, cpuct, temp_threshold, seed=0, auto_reset=False):
-        cfg = _lib.SelfPlayConfig(int(num_sims), int(temp_threshold), int(bool(auto_reset)), 0, float(cpuct),
+    def selfplay_configure(self, num_sims, cpuct, temp_threshold, seed=0, auto_reset=False, discard_records=False):
+        cfg = _lib.SelfPlayConfig(int(num_sims), int(temp_threshold), int(bool(auto_reset)), int(bool(discard_records)),
+                                  float(cpuct),
                                   int(seed) & (2 ** 64 - 1))
         check(self.lib.tc_selfplay_configure(self.handle, ctypes.byref(cfg)))
 
@@ -180,7 +182,7 @@ class Engine:
         return s.as_dict()
 
     def selfplay_drain(self):
-        cap = self.num_envs * 96
+        cap = self.num_envs * 256
         buf = np.zeros(cap, dtype=_lib.EXAMPLE_DTYPE)
         n = ctypes.c_int(0)
         check(self.lib.tc_selfplay_drain(self.handle, cap, ptr(buf), ctypes.byref(n)))

@@ -100,9 +100,10 @@ def test_counts_match_oracle_with_ties_zero_priors_and_draw_values(make_args):
 
 
 def test_deep_search_transpositions(make_args):
-    # many simulations from few positions: transpositions and deep paths (> 32 levels late in the game)
-    gpu, cpu = play_both(make_args, envs=2, sims=400, cpuct=0.5, salt=5, pi_levels=0, v_levels=0, seed=3, max_plies=12)
-    assert gpu.engine.stats()["transpositions"] > 0
+    # a configuration where the reference search merges transposed positions (found with the oracle:
+    # first use of an edge whose successor is already a node); the engine must merge the same ones
+    gpu, cpu = play_both(make_args, envs=2, sims=300, cpuct=4.0, salt=6, pi_levels=2, v_levels=0, seed=3, max_plies=12)
+    assert gpu.engine.stats()["transpositions"] == cpu.stat_transpositions > 0
 
 
 def test_none_and_terminal_roots(make_args, golden):

@@ -68,10 +68,33 @@ def test_auto_reset_keeps_all_envs_busy():
     envs, sims = 64, 8
     eng = tb.Engine(envs, sims * 82 + 64, hash_salt=2)
     eng.selfplay_begin(sims, 2.4, 10, seed=1, auto_reset=True)
-    eng.selfplay_step(150)
-    eng.selfplay_sync()
+    recs = []
+    for _ in range(3):
+        eng.selfplay_step(50)
+        eng.selfplay_sync()
+        recs.append(eng.selfplay_drain())
+    recs = np.concatenate(recs)
     st = eng.selfplay_stats()
     assert st["plies"] == envs * 150 and st["games_finished"] >= envs
-    recs = eng.selfplay_drain()
     assert len(recs) > 0 and (recs["finished"] > 0).all()
     assert set(np.unique(recs["game"])) >= {0, 1}
+    # every finished game is complete: plies 0..n-1 of (env, game) are all there
+    for env in range(0, envs, 7):
+        mine = recs[(recs["env"] == env) & (recs["game"] == 0)]
+        assert sorted(mine["ply"]) == list(range(len(mine))) and len(mine) >= 17
+
+
+def test_record_buffer_overflow_is_loud_and_discard_mode_is_silent():
+    envs, sims = 32, 2
+    eng = tb.Engine(envs, sims * 82 + 64, hash_salt=2)
+    eng.selfplay_begin(sims, 2.4, 10, seed=1, auto_reset=True)
+    eng.selfplay_step(600)                  # ~19k records into a buffer of 32*256
+    eng.selfplay_sync()
+    with pytest.raises(tb._lib.TacultError) as err:
+        eng.selfplay_drain()
+    assert err.value.code == tb._lib.TC_ECAPACITY
+    assert len(eng.selfplay_drain()) == 0   # buffer restarted empty
+    eng.selfplay_configure(sims, 2.4, 10, seed=1, auto_reset=True, discard_records=True)
+    eng.selfplay_step(600)
+    eng.selfplay_sync()
+    assert len(eng.selfplay_drain()) == 0
