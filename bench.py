@@ -267,8 +267,10 @@ def run_b200(a):
     prof = eng.profile_read()
     eng.profile_enable(False)
     kp1 = eng.stats()
-    roof, kernels = roofline(prof, kp0, kp1, a, evaluator, flops_per_eval(NET["channels"], NET["num_residual_blocks"],
-                                                                          NET["embedding_size"]))
+    roof, kernels = None, {}
+    if a.profile_plies > 0:
+        roof, kernels = roofline(prof, kp0, kp1, a, evaluator, flops_per_eval(NET["channels"], NET["num_residual_blocks"],
+                                                                              NET["embedding_size"]))
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     e2e = None
