@@ -168,6 +168,10 @@ int tc_forward_states(tc_engine *e, int evaluator, int batch, const uint32_t *st
 int tc_forward_states_dev(tc_engine *e, int evaluator, int batch, const uint32_t *states_dev, float *pi_dev,
                           float *v_dev);
 
+/* test hook: trunk activations after conv_in and the first n_convs residual-block convolutions,
+ * float32 [batch][81][channels] (NHWC), for either network evaluator */
+int tc_debug_trunk(tc_engine *e, int evaluator, int batch, const uint32_t *states_host, int n_convs, float *out_host);
+
 /* ---- device-resident self-play driver: Coach.executeEpisode semantics
  *      (/root/reference/src/tacult/base/coach.py:87-157) without host round trips ------------------------- */
 #define TC_SP_DISCARD_RECORDS 1

@@ -565,6 +565,27 @@ extern "C" int tc_forward_states_dev(tc_engine *e, int evaluator, int batch, con
     return run_forward(e, evaluator, batch, states_dev, nullptr, pi_dev, v_dev, nullptr);
 }
 
+extern "C" int tc_debug_trunk(tc_engine *e, int evaluator, int batch, const uint32_t *states_host, int n_convs,
+                              float *out_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(e->have_weights, TC_ESTATE, "tc_debug_trunk: tc_load_weights has not been called");
+    TC_CHECK(batch >= 1 && batch <= e->net32.capacity && states_host && out_host && n_convs >= 0, TC_EINVAL,
+             "tc_debug_trunk: bad argument (batch must be <= num_envs)");
+    const size_t n = (size_t)batch * 81 * e->folded.d.channels;
+    DevBuf<uint32_t> st;
+    DevBuf<float> out;
+    TC_CUDA(st.alloc((size_t)batch * 8));
+    TC_CUDA(out.alloc(n));
+    TC_CUDA(cudaMemcpyAsync(st.p, states_host, (size_t)batch * 32, cudaMemcpyHostToDevice, e->stream));
+    if (evaluator == TC_EVAL_NET_F32) TC_TRY(e->net32.debug_trunk(batch, st.p, n_convs, out.p, e->stream));
+    else TC_TRY(debug_trunk_bf16(e->net16, batch, st.p, n_convs, out.p, e->stream));
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaMemcpyAsync(out_host, out.p, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    return TC_OK;
+}
+
 // ---- self-play driver --------------------------------------------------------------------------
 extern "C" int tc_selfplay_begin(tc_engine *e, const tc_selfplay_config *cfg)
 {

@@ -33,6 +33,7 @@ struct NetF32 {
     // live batch size on the device, `batch` is the launch bound.  Returns the number of kernels launched.
     int forward(int batch, const int *count_dev, const uint32_t *states, const float *obs, float *pi, float *v,
                 float *logits, cudaStream_t st, Profiler *prof = nullptr);
+    int debug_trunk(int batch, const uint32_t *states, int n_convs, float *out, cudaStream_t st);
 };
 
 size_t blob_floats(const tc_net_desc &d);

@@ -1,24 +1,711 @@
-// bf16 tcgen05/TMEM forward — placeholder until the tensor-core trunk lands (next milestone).
+// bf16 tensor-core forward of the dual-head ResNet ("production mode": within 2e-2 of the reference net).
+// Graph: /root/reference/src/tacult/network.py:81-102.
+//
+// Every 3x3 convolution of the trunk and fc1 run as tcgen05 GEMMs with fp32 accumulators in TMEM, operands
+// staged in shared memory by TMA (cp.async.bulk.tensor, 32/64/128-byte swizzle), BN-fold + bias + residual +
+// ReLU fused in the TMEM->register epilogue.
+//
+// Implicit GEMM without an im2col buffer: activations live in HBM as bf16 rows [row][C] in a padded, stacked
+// layout — position b occupies 100 rows, cell (r,c) at row 16 + 100 b + 10 r + c; the 10th column of every
+// board row and the 10 rows after each position are zero and never written.  A 3x3 tap (dy,dx) is then a pure
+// row offset 10 dy + dx, so the A tile of a tap is ONE 2-D TMA box at a shifted row coordinate and the zero
+// halo comes for free.  81 of every 100 GEMM rows are real outputs.
+//
+// Kernel anatomy (persistent, warp specialised, one elected thread per async role):
+//   warp 0  TMA producer      smem ring:  full[s] / empty[s] mbarriers
+//   warp 1  tcgen05.mma issue TMEM ring:  tmem_full[2] / tmem_empty[2]   (also allocates / frees TMEM)
+//   warps 2-5 epilogue        tcgen05.ld 32 lanes x 32 columns per warp, one GEMM row per thread
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "nn_bf16.cuh"
+#include "rules.cuh"
 
 namespace tc {
 
-struct NetBF16Impl {};
+constexpr int PAD0 = 16;            // zero rows in front of position 0 (>= 11, the largest tap offset)
+constexpr int ROWS_PER_POS = 100;
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
 
-NetBF16::~NetBF16() { delete impl; }
+enum { OUT_PADDED_BF16 = 0, OUT_COMPACT_BF16 = 1, OUT_F32 = 2 };
 
-int NetBF16::upload(const FoldedNet &, int)
+struct GemmParams {
+    const int *count_dev;     // live positions (may be null)
+    int batch;                // launch bound on positions
+    int rows_per_unit;        // GEMM rows per position: 100 (conv) or 1 (fc1)
+    int taps;                 // 9 (conv) or 1
+    int k_chunks;             // BLOCK_K chunks per tap
+    int block_n;              // N per tile (multiple of 16, <= 256)
+    int n_blocks;             // N tiles
+    int a_row0;               // first A row of GEMM row 0 (PAD0 for conv, 0 for fc1)
+    int b_tap_rows;           // rows of the weight tensor per tap
+    int stages;
+    int mode;
+    int relu;
+    int ldc;                  // output row length in elements (C or E)
+    const float *bias;
+    const __nv_bfloat16 *residual;   // padded layout, may be null
+    void *out;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    loaded = false;
-    why_not = "bf16 tensor-core path not built yet";
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of SW bytes (= BLOCK_K bf16), SW-byte swizzle as written by TMA.
+// Fields: start address >> 4 [0,14), LBO [16,30) unused for one swizzle atom along K, SBO = 8 rows * SW [32,46),
+// version 1 [46,48), layout type [61,64): 2 = 128B, 4 = 64B, 6 = 32B swizzle.
+template <int SW>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+{
+    constexpr uint64_t layout = SW == 128 ? 2ull : (SW == 64 ? 4ull : 6ull);
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((8u * SW) >> 4) << 32;
+    d |= 1ull << 46;
+    d |= layout << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = f32 [4,6)=1, A = B = bf16 [7,10)=[10,13)=1, both K-major, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_instr_desc(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ int live_count(const int *count_dev, int batch)
+{
+    int n = batch;
+    if (count_dev) n = min(n, *count_dev);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM / implicit-conv kernel
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_K>
+__global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmB, GemmParams P)
+{
+    constexpr int SW = BLOCK_K * 2;
+    constexpr int A_BYTES = 128 * SW;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = (P.block_n * SW + 1023) & ~1023;
+    const int stage_bytes = A_BYTES + b_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)P.stages * stage_bytes);
+    uint64_t *full = bars, *empty = bars + MAX_STAGES, *tfull = bars + 2 * MAX_STAGES, *tempty = bars + 2 * MAX_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int count = live_count(P.count_dev, P.batch);
+    const int m_total = count * P.rows_per_unit;
+    const int m_tiles = (m_total + 127) >> 7;
+    const int n_tiles = m_tiles * P.n_blocks;
+    const int num_kb = P.taps * P.k_chunks;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * P.block_n) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int mt = tile / P.n_blocks, nb = tile - mt * P.n_blocks;
+                const int a_row = P.a_row0 + 128 * mt;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / P.k_chunks, kc = kb - tap * P.k_chunks;
+                    const int shift = P.taps == 9 ? (tap / 3 - 1) * 10 + (tap % 3 - 1) : 0;
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(full + stage, (uint32_t)(A_BYTES + P.block_n * SW));
+                    tma_load_2d(sa, &tmA, full + stage, kc * BLOCK_K, a_row + shift);
+                    tma_load_2d(sa + A_BYTES, &tmB, full + stage, kc * BLOCK_K, tap * P.b_tap_rows + nb * P.block_n);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_instr_desc(P.block_n);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty + as, aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.block_n);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        umma_bf16(d_tmem, make_smem_desc<SW>(a_addr + 32 * k), make_smem_desc<SW>(b_addr + 32 * k), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    umma_commit(empty + stage);           // smem slot is free once these MMAs have read it
+                    if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull + as);                  // accumulator complete
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias / residual / ReLU -> HBM =====
+        const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mt = tile / P.n_blocks, nb = tile - mt * P.n_blocks;
+            const int n0 = nb * P.block_n;
+            const int q = 128 * mt + 32 * quarter + lane;      // GEMM row of this thread
+            bool valid;
+            size_t out_row;
+            if (P.mode == OUT_F32) {
+                valid = q < m_total;
+                out_row = (size_t)q;
+            } else {
+                const int b = q / ROWS_PER_POS, rem = q - b * ROWS_PER_POS;
+                const int r = rem / 10, c = rem - 10 * r;
+                valid = b < count && rem < 90 && c != 9;
+                out_row = P.mode == OUT_PADDED_BF16 ? (size_t)(PAD0 + q) : (size_t)(b * 81 + r * 9 + c);
+            }
+            mbar_wait(tfull + as, aphase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(as * P.block_n);
+            const int cw = P.block_n < 32 ? 16 : 32;
+            for (int c0 = 0; c0 < P.block_n; c0 += cw) {
+                uint32_t acc[32];
+                if (cw == 32) tmem_ld32(t_base + (uint32_t)c0, acc); else tmem_ld16(t_base + (uint32_t)c0, acc);
+                tmem_ld_wait();
+                if (valid) {
+                    const float *bias = P.bias + n0 + c0;
+                    if (P.mode == OUT_F32) {
+                        float *o = reinterpret_cast<float *>(P.out) + out_row * P.ldc + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (j >= cw) break;
+                            float4 v;
+                            v.x = __uint_as_float(acc[j]) + __ldg(bias + j);
+                            v.y = __uint_as_float(acc[j + 1]) + __ldg(bias + j + 1);
+                            v.z = __uint_as_float(acc[j + 2]) + __ldg(bias + j + 2);
+                            v.w = __uint_as_float(acc[j + 3]) + __ldg(bias + j + 3);
+                            if (P.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4 *>(o + j) = v;
+                        }
+                    } else {
+                        __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(P.out) + out_row * P.ldc + n0 + c0;
+                        const __nv_bfloat16 *res = P.residual ? P.residual + (size_t)(PAD0 + q) * P.ldc + n0 + c0 : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (j >= cw) break;
+                            float v[8];
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]) + __ldg(bias + j + t);
+                            if (res) {
+                                uint4 rv = *reinterpret_cast<const uint4 *>(res + j);
+                                const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    float2 f = __bfloat1622float2(rp[t]);
+                                    v[2 * t] += f.x;
+                                    v[2 * t + 1] += f.y;
+                                }
+                            }
+                            uint4 ov;
+                            __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                float a = v[2 * t], b2 = v[2 * t + 1];
+                                if (P.relu) { a = fmaxf(a, 0.f); b2 = fmaxf(b2, 0.f); }
+                                op[t] = __floats2bfloat162_rn(a, b2);
+                            }
+                            *reinterpret_cast<uint4 *>(o + j) = ov;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + as);
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// conv_in (in_planes -> C) + folded BN + ReLU on CUDA cores (K = 36: not worth a tensor tile), writing the
+// padded bf16 layout (or the compact one when the net has no residual block).  One block per position.
+__global__ void __launch_bounds__(256) k_stem_bf16(int batch, const int *__restrict__ count_dev,
+                                                   const uint32_t *__restrict__ states, const float *__restrict__ obs,
+                                                   int in_planes, int C, const float *__restrict__ w,
+                                                   const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
+                                                   int compact)
+{
+    extern __shared__ float s_in[];        // [in_planes][121], zero border
+    const int row = blockIdx.x;
+    if (row >= live_count(count_dev, batch)) return;
+    for (int i = threadIdx.x; i < in_planes * 121; i += blockDim.x) s_in[i] = 0.f;
+    __syncthreads();
+    if (states) {
+        if (threadIdx.x < 81) {
+            uint32_t wd[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wd[k] = states[8 * (size_t)row + k];
+            Pos p = unpack(wd);
+            Summary s = summarize(p);
+            uint32_t lw[3];
+            legal_words(p, s, lw);
+            int a = threadIdx.x, cell = (a / 9 + 1) * 11 + a % 9 + 1;
+            bool mine = action_bit(p.mine, a), occ = action_bit(p.occ, a);
+            s_in[cell] = mine ? 1.f : 0.f;
+            s_in[121 + cell] = (occ && !mine) ? 1.f : 0.f;
+            s_in[242 + cell] = action_bit(lw, a) ? 1.f : 0.f;
+            s_in[363 + cell] = 1.f;
+        }
+    } else {
+        for (int i = threadIdx.x; i < in_planes * 81; i += blockDim.x) {
+            int pl = i / 81, a = i % 81;
+            s_in[pl * 121 + (a / 9 + 1) * 11 + a % 9 + 1] = obs[(size_t)row * in_planes * 81 + i];
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 81 * C; idx += blockDim.x) {
+        int p = idx / C, c = idx % C;
+        int base = (p / 9) * 11 + p % 9;
+        float acc = bias[c];
+        for (int pl = 0; pl < in_planes; ++pl) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                acc = fmaf(s_in[pl * 121 + base + (t / 3) * 11 + t % 3], w[(t * in_planes + pl) * C + c], acc);
+        }
+        size_t orow = compact ? (size_t)row * 81 + p : (size_t)PAD0 + (size_t)row * ROWS_PER_POS + (p / 9) * 10 + p % 9;
+        out[orow * C + c] = __float2bfloat16_rn(fmaxf(acc, 0.f));
+    }
+}
+
+// debug / test helper: padded or compact bf16 activations -> f32 [row][81][C]
+__global__ void k_unpad_to_f32(int batch, int C, const __nv_bfloat16 *__restrict__ in, int compact, float *__restrict__ out)
+{
+    size_t n = (size_t)batch * 81 * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        size_t bp = i / C;
+        int p = (int)(bp % 81);
+        size_t b = bp / 81;
+        size_t row = compact ? bp : (size_t)PAD0 + b * ROWS_PER_POS + (p / 9) * 10 + p % 9;
+        out[i] = __bfloat162float(in[row * C + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous), box [box_rows][box_cols], swizzle = box_cols * 2 bytes
+static int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    TC_CHECK(fn != nullptr, TC_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TC_CHECK(r == CUDA_SUCCESS, TC_ECUDA, "cuTensorMapEncodeTiled failed with code %d (rows %llu cols %llu box %u x %u)",
+             (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols);
     return TC_OK;
 }
 
-int NetBF16::forward(int, const int *, const uint32_t *, const float *, float *, float *, float *, cudaStream_t,
-                     Profiler *)
+struct NetBF16Impl {
+    tc_net_desc d{};
+    int capacity = 0;
+    int block_k = 0;            // conv K chunk (channels): 16, 32 or 64
+    size_t act_rows = 0;
+    DevBuf<__nv_bfloat16> act[3];          // padded layout
+    DevBuf<__nv_bfloat16> flat;            // compact [cap][81*C], fc1 input
+    DevBuf<float> emb;                     // [cap][E]
+    DevBuf<float> stem_w, stem_b;
+    std::vector<DevBuf<__nv_bfloat16>> conv_w;   // [9][Cout][Cin]
+    std::vector<DevBuf<float>> conv_b;
+    DevBuf<__nv_bfloat16> fc1_w;           // [E][81*C], k = p*C + c
+    DevBuf<float> fc1_b, head_w, head_b;
+    CUtensorMap map_act[3], map_flat, map_fc1;
+    std::vector<CUtensorMap> map_conv_w;
+    int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
+    int sm_count = SM_COUNT;
+};
+
+NetBF16::~NetBF16() { delete impl; }
+
+static size_t gemm_smem_bytes(int block_k, int block_n, int stages)
 {
-    set_error("bf16 evaluator: %s", why_not.c_str());
-    return TC_ESTATE;
+    size_t a = 128 * block_k * 2, b = ((size_t)block_n * block_k * 2 + 1023) & ~(size_t)1023;
+    return 1024 + stages * (a + b) + (2 * MAX_STAGES + 4) * 8 + 16;
+}
+
+static int pick_stages(int block_k, int block_n, size_t budget)
+{
+    int s = MAX_STAGES;
+    while (s > 2 && gemm_smem_bytes(block_k, block_n, s) > budget) --s;
+    return s;
+}
+
+template <typename T>
+static int upload(DevBuf<T> &dst, const std::vector<T> &src)
+{
+    TC_CUDA(dst.alloc(src.size()));
+    TC_CUDA(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return TC_OK;
+}
+
+static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
+{
+    m.d = f.d;
+    m.capacity = cap;
+    const int C = f.d.channels, E = f.d.embedding_size, I = f.d.in_planes;
+    m.block_k = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&m.sm_count, cudaDevAttrMultiProcessorCount, dev);
+
+    std::vector<float> t((size_t)9 * I * C);
+    for (int co = 0; co < C; ++co)
+        for (int ci = 0; ci < I; ++ci)
+            for (int tap = 0; tap < 9; ++tap) t[((size_t)tap * I + ci) * C + co] = f.stem_w[((size_t)co * I + ci) * 9 + tap];
+    TC_TRY(upload(m.stem_w, t));
+    TC_TRY(upload(m.stem_b, f.stem_b));
+
+    const size_t L = f.conv_w.size();
+    m.conv_w.clear();
+    m.conv_b.clear();
+    m.conv_w.resize(L);
+    m.conv_b.resize(L);
+    m.map_conv_w.resize(L);
+    std::vector<__nv_bfloat16> wb((size_t)9 * C * C);
+    for (size_t l = 0; l < L; ++l) {
+        for (int tap = 0; tap < 9; ++tap)
+            for (int co = 0; co < C; ++co)
+                for (int ci = 0; ci < C; ++ci)
+                    wb[((size_t)tap * C + co) * C + ci] = __float2bfloat16_rn(f.conv_w[l][((size_t)co * C + ci) * 9 + tap]);
+        TC_TRY(upload(m.conv_w[l], wb));
+        TC_TRY(upload(m.conv_b[l], f.conv_b[l]));
+        TC_TRY(make_map(&m.map_conv_w[l], m.conv_w[l].p, (uint64_t)9 * C, C, (uint32_t)C, (uint32_t)m.block_k));
+    }
+    // fc1: [E][c*81+p] (NCHW flatten, network.py:92) -> [E][p*C+c] to match the NHWC activations
+    std::vector<__nv_bfloat16> fb((size_t)E * 81 * C);
+    for (int e = 0; e < E; ++e)
+        for (int c = 0; c < C; ++c)
+            for (int p = 0; p < 81; ++p)
+                fb[(size_t)e * 81 * C + (size_t)p * C + c] = __float2bfloat16_rn(f.fc1_w[(size_t)e * 81 * C + (size_t)c * 81 + p]);
+    TC_TRY(upload(m.fc1_w, fb));
+    TC_TRY(upload(m.fc1_b, f.fc1_b));
+    std::vector<float> hw((size_t)E * 82), hb(f.pi_b);
+    for (int k = 0; k < E; ++k) {
+        for (int o = 0; o < 81; ++o) hw[(size_t)k * 82 + o] = f.pi_w[(size_t)o * E + k];
+        hw[(size_t)k * 82 + 81] = f.v_w[k];
+    }
+    hb.push_back(f.v_b[0]);
+    TC_TRY(upload(m.head_w, hw));
+    TC_TRY(upload(m.head_b, hb));
+
+    m.act_rows = (size_t)PAD0 + (size_t)cap * ROWS_PER_POS + 128 + 32;
+    for (int i = 0; i < 3; ++i) {
+        TC_CUDA(m.act[i].alloc(m.act_rows * C));
+        TC_CUDA(cudaMemset(m.act[i].p, 0, m.act[i].bytes()));       // pad rows stay zero for ever
+        TC_TRY(make_map(&m.map_act[i], m.act[i].p, m.act_rows, C, 128, (uint32_t)m.block_k));
+    }
+    const size_t flat_rows = std::max(cap, 128);
+    TC_CUDA(m.flat.alloc(flat_rows * 81 * C));
+    TC_CUDA(cudaMemset(m.flat.p, 0, m.flat.bytes()));
+    TC_CUDA(m.emb.alloc((size_t)cap * E));
+    m.fc1_block_n = E % 64 == 0 ? 64 : (E % 32 == 0 ? 32 : 16);
+    TC_TRY(make_map(&m.map_flat, m.flat.p, (uint64_t)flat_rows, (uint64_t)81 * C, 128, 64));
+    TC_TRY(make_map(&m.map_fc1, m.fc1_w.p, (uint64_t)E, (uint64_t)81 * C, (uint32_t)m.fc1_block_n, 64));
+
+    const size_t budget = 200 * 1024;
+    m.conv_stages = pick_stages(m.block_k, C, C <= 64 ? 48 * 1024 : budget);
+    m.fc1_stages = pick_stages(64, m.fc1_block_n, 96 * 1024);
+    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    return TC_OK;
+}
+
+int NetBF16::upload(const FoldedNet &f, int capacity)
+{
+    loaded = false;
+    const int C = f.d.channels, E = f.d.embedding_size;
+    if (!(C == 16 || (C % 32 == 0 && C <= 256))) { why_not = "bf16 tensor path needs channels == 16 or a multiple of 32 up to 256"; return TC_OK; }
+    if (E % 16 != 0) { why_not = "bf16 tensor path needs embedding_size to be a multiple of 16"; return TC_OK; }
+    if (((size_t)81 * C * 2) % 16 != 0) { why_not = "fc1 row pitch must be a multiple of 16 bytes"; return TC_OK; }
+    delete impl;
+    impl = new NetBF16Impl();
+    int rc = upload_impl(*impl, f, capacity);
+    if (rc != TC_OK) {
+        why_not = tc_last_error();
+        delete impl;
+        impl = nullptr;
+        return rc;
+    }
+    loaded = true;
+    why_not.clear();
+    return TC_OK;
+}
+
+static void launch_gemm(const NetBF16Impl &m, int block_k, const CUtensorMap &a, const CUtensorMap &b, const GemmParams &P,
+                        int max_tiles, cudaStream_t st)
+{
+    const size_t smem = gemm_smem_bytes(block_k, P.block_n, P.stages);
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * P.block_n) tmem_cols <<= 1;
+    int per_sm = (int)std::min<size_t>(4, (220 * 1024) / smem);
+    per_sm = std::min(per_sm, 512 / tmem_cols);      // every resident CTA must get its TMEM columns
+    if (per_sm < 1) per_sm = 1;
+    int grid = std::min(max_tiles, m.sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    if (block_k == 64) k_gemm_tc<64><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+    else if (block_k == 32) k_gemm_tc<32><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+    else k_gemm_tc<16><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+}
+
+void launch_heads_f32(int batch, const int *count_dev, int E, const float *emb, const float *W, const float *bias,
+                      float *pi, float *v, float *logits, cudaStream_t st);
+
+// runs the stem and the first n_convs trunk convolutions; returns the index of the buffer holding the result
+// (or -1 when the result is in `flat`).  n_convs == all: the last conv writes the compact fc1 input.
+static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint32_t *states, const float *obs,
+                     int n_convs, bool to_flat, cudaStream_t st, Profiler *prof, int &launches)
+{
+    const int C = m.d.channels, I = m.d.in_planes;
+    const int total = 2 * m.d.num_residual_blocks;
+    const bool stem_flat = to_flat && n_convs == 0;
+    prof->begin(TC_K_NN_STEM, st);
+    k_stem_bf16<<<batch, 256, sizeof(float) * I * 121, st>>>(batch, count_dev, states, obs, I, C, m.stem_w.p, m.stem_b.p,
+                                                             stem_flat ? m.flat.p : m.act[0].p, stem_flat ? 1 : 0);
+    prof->end(st);
+    ++launches;
+    if (stem_flat) return -1;
+    int x = 0, y = 1, z = 2;
+    const int max_tiles = ((batch * ROWS_PER_POS + 127) / 128);
+    int cur = x;
+    for (int l = 0; l < n_convs && l < total; ++l) {
+        const bool second = (l & 1) != 0;
+        const bool last = to_flat && l == n_convs - 1;
+        GemmParams P{};
+        P.count_dev = count_dev;
+        P.batch = batch;
+        P.rows_per_unit = ROWS_PER_POS;
+        P.taps = 9;
+        P.k_chunks = C / m.block_k;
+        P.block_n = C;
+        P.n_blocks = 1;
+        P.a_row0 = PAD0;
+        P.b_tap_rows = C;
+        P.stages = m.conv_stages;
+        P.mode = last ? OUT_COMPACT_BF16 : OUT_PADDED_BF16;
+        P.relu = 1;
+        P.ldc = C;
+        P.bias = m.conv_b[l].p;
+        const int src = second ? y : x;
+        const int dst = second ? z : y;
+        P.residual = second ? m.act[x].p : nullptr;
+        P.out = last ? (void *)m.flat.p : (void *)m.act[dst].p;
+        prof->begin(TC_K_NN_CONV, st);
+        launch_gemm(m, m.block_k, m.map_act[src], m.map_conv_w[l], P, max_tiles, st);
+        prof->end(st);
+        ++launches;
+        cur = dst;
+        if (second) { int t = x; x = z; z = t; }
+        if (last) return -1;
+    }
+    return cur;
+}
+
+int NetBF16::forward(int batch, const int *count_dev, const uint32_t *states, const float *obs, float *pi, float *v,
+                     float *logits, cudaStream_t st, Profiler *prof)
+{
+    if (!loaded || !impl) {
+        set_error("bf16 evaluator: %s", why_not.c_str());
+        return TC_ESTATE;
+    }
+    NetBF16Impl &m = *impl;
+    Profiler none;
+    if (!prof) prof = &none;
+    int launches = 0;
+    const int C = m.d.channels, E = m.d.embedding_size;
+    run_trunk(m, batch, count_dev, states, obs, 2 * m.d.num_residual_blocks, true, st, prof, launches);
+    GemmParams P{};
+    P.count_dev = count_dev;
+    P.batch = batch;
+    P.rows_per_unit = 1;
+    P.taps = 1;
+    P.k_chunks = (81 * C + 63) / 64;
+    P.block_n = m.fc1_block_n;
+    P.n_blocks = E / m.fc1_block_n;
+    P.a_row0 = 0;
+    P.b_tap_rows = 0;
+    P.stages = m.fc1_stages;
+    P.mode = OUT_F32;
+    P.relu = 1;
+    P.ldc = E;
+    P.bias = m.fc1_b.p;
+    P.residual = nullptr;
+    P.out = m.emb.p;
+    prof->begin(TC_K_NN_FC1, st);
+    launch_gemm(m, 64, m.map_flat, m.map_fc1, P, ((batch + 127) / 128) * P.n_blocks, st);
+    prof->end(st);
+    prof->begin(TC_K_NN_HEADS, st);
+    launch_heads_f32(batch, count_dev, E, m.emb.p, m.head_w.p, m.head_b.p, pi, v, logits, st);
+    prof->end(st);
+    launches += 2;
+    return launches;
+}
+
+// test hook (tc_debug_trunk): activations after the stem and n_convs convolutions, as f32 [batch][81][C]
+int debug_trunk_bf16(NetBF16 &net, int batch, const uint32_t *states_dev, int n_convs, float *out_dev, cudaStream_t st)
+{
+    if (!net.loaded || !net.impl) {
+        set_error("bf16 evaluator: %s", net.why_not.c_str());
+        return TC_ESTATE;
+    }
+    Profiler none;
+    int launches = 0;
+    int buf = run_trunk(*net.impl, batch, nullptr, states_dev, nullptr, n_convs, false, st, &none, launches);
+    k_unpad_to_f32<<<256, 256, 0, st>>>(batch, net.impl->d.channels, net.impl->act[buf].p, 0, out_dev);
+    return TC_OK;
 }
 
 }  // namespace tc

@@ -24,4 +24,6 @@ struct NetBF16 {
                 float *logits, cudaStream_t st, Profiler *prof = nullptr);
 };
 
+int debug_trunk_bf16(NetBF16 &net, int batch, const uint32_t *states_dev, int n_convs, float *out_dev, cudaStream_t st);
+
 }  // namespace tc

@@ -441,4 +441,33 @@ int NetF32::forward(int batch, const int *count_dev, const uint32_t *states, con
     return launches;
 }
 
+void launch_heads_f32(int batch, const int *count_dev, int E, const float *emb, const float *W, const float *bias,
+                      float *pi, float *v, float *logits, cudaStream_t st)
+{
+    k_heads_f32<<<ceil_div(batch, 8), 256, sizeof(float) * 8 * E, st>>>(batch, count_dev, E, emb, W, bias, pi, v, logits);
+}
+
+// test hook (tc_debug_trunk): activations after the stem and n_convs convolutions, f32 [batch][81][C]
+int NetF32::debug_trunk(int batch, const uint32_t *states, int n_convs, float *out, cudaStream_t st)
+{
+    const int C = d.channels, I = d.in_planes;
+    k_stem_f32<<<batch, 256, sizeof(float) * I * 121, st>>>(batch, nullptr, states, nullptr, I, C, stem_w.p, stem_b.p, act[0].p);
+    const int CK = C < 32 ? C : 32, CT = CK;
+    dim3 cgrid(ceil_div(batch, CONV_G), C / CT);
+    const size_t csm = conv_smem_bytes(C);
+    float *x = act[0].p, *y = act[1].p, *z = act[2].p, *cur = x;
+    for (int l = 0; l < n_convs && l < 2 * d.num_residual_blocks; ++l) {
+        if ((l & 1) == 0) {
+            k_conv3x3_f32<<<cgrid, CONV_THREADS, csm, st>>>(batch, nullptr, C, CK, CT, x, conv_w[l].p, conv_b[l].p, nullptr, y);
+            cur = y;
+        } else {
+            k_conv3x3_f32<<<cgrid, CONV_THREADS, csm, st>>>(batch, nullptr, C, CK, CT, y, conv_w[l].p, conv_b[l].p, x, z);
+            cur = z;
+            float *t = x; x = z; z = t;
+        }
+    }
+    TC_CUDA(cudaMemcpyAsync(out, cur, (size_t)batch * 81 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return TC_OK;
+}
+
 }  // namespace tc

@@ -99,6 +99,12 @@ class Engine:
         check(self.lib.tc_forward_states(self.handle, int(evaluator), b, ptr(states), ptr(pi), ptr(v)))
         return pi, v
 
+    def debug_trunk(self, states, n_convs, evaluator=_lib.EVAL_NET_F32):
+        states = np.ascontiguousarray(states, dtype=np.uint32).reshape(-1, 8)
+        out = np.empty((states.shape[0], 81, self.net_desc.channels), dtype=np.float32)
+        check(self.lib.tc_debug_trunk(self.handle, int(evaluator), states.shape[0], ptr(states), int(n_convs), ptr(out)))
+        return out
+
     # -- search --------------------------------------------------------------------------------
     def reset(self, env=-1):
         check(self.lib.tc_reset(self.handle, int(env)))
