@@ -219,7 +219,10 @@ def run_b200(a):
 
     E, sims = a.envs, a.sims
     eng = tb.Engine(E, sims * 82 + 64, device=local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: the engine launches on it, and the timing events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     eng.load_weights(random_state_dict(0, **NET))
     evaluator = a.evaluator

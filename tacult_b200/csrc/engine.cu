@@ -505,11 +505,11 @@ static int run_forward(tc_engine *e, int evaluator, int batch, const uint32_t *s
         const float *o = obs_dev ? obs_dev + (size_t)r0 * e->folded.d.in_planes * 81 : nullptr;
         float *lg = logits_dev ? logits_dev + (size_t)r0 * 81 : nullptr;
         if (evaluator == TC_EVAL_NET_F32) {
-            e->launches += e->net32.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream);
+            e->launches += e->net32.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream, &e->prof);
         } else {
             TC_CHECK(e->net16.loaded, TC_ESTATE, "bf16 evaluator not available for this network shape: %s",
                      e->net16.why_not.c_str());
-            int n = e->net16.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream);
+            int n = e->net16.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream, &e->prof);
             if (n < 0) return n;
             e->launches += n;
         }

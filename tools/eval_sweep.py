@@ -36,7 +36,8 @@ def main():
     flops = flops_per_eval(C, B, E)
     ev = tb._lib.EVAL_NET_BF16 if a.evaluator == "bf16" else tb._lib.EVAL_NET_F32
     sd = random_state_dict(0, C, B, E)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # non-default stream shared by the engine and the timing events
+    torch.cuda.set_stream(stream)
     for batch in [int(x) for x in a.batches.split(",")]:
         eng = tb.Engine(batch, 2)
         eng.set_stream(stream.cuda_stream)
