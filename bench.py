@@ -200,6 +200,7 @@ def run_b200(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_dev = local
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -280,6 +281,21 @@ def run_b200(a):
     if not a.skip_e2e:
         e2e = run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world)
 
+    # ---- N>1: the one exchange step — finished trajectories all-gathered over NCCL (outside the timed region)
+    gathered = None
+    if world > 1:
+        from tacult_b200.distributed import all_gather_records
+        eng.selfplay_configure(sims, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True)
+        eng.selfplay_drain()
+        eng.selfplay_step(2)
+        eng.selfplay_sync()
+        local_recs = eng.selfplay_drain()
+        t0 = time.perf_counter()
+        allrec = all_gather_records(local_recs, device=torch.device("cuda", local_dev))
+        torch.cuda.synchronize()
+        gathered = {"records_local": int(len(local_recs)), "records_all_ranks": int(len(allrec)),
+                    "ms": 1e3 * (time.perf_counter() - t0), "bytes_per_record": 216}
+
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu_baseline:
         rate, n, dt, _ = cpu_selfplay_rate(64, 25, seconds=a.cpu_seconds)
@@ -298,7 +314,7 @@ def run_b200(a):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roof, "kernels": kernels,
-            "e2e": e2e, "cpu_baseline": cpu,
+            "e2e": e2e, "cpu_baseline": cpu, "trajectory_all_gather": gathered,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

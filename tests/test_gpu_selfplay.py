@@ -98,3 +98,40 @@ def test_record_buffer_overflow_is_loud_and_discard_mode_is_silent():
     eng.selfplay_step(600)
     eng.selfplay_sync()
     assert len(eng.selfplay_drain()) == 0
+
+
+def test_records_to_training_examples_match_coach_format():
+    """(obs, pi, z) tuples incl. the 8 symmetries, as coach.py:136-149 builds them, from the device records."""
+    from tacult_b200.selfplay import arrays_to_examples, records_to_arrays
+    envs, sims, threshold, salt = 4, 16, 5, 77
+    eng, recs = run_games(envs, sims, threshold, seed=9, salt=salt)
+    obs, pi, z = records_to_arrays(recs, augment=True)
+    assert obs.shape == (8 * len(recs), 4, 9, 9) and pi.shape == (8 * len(recs), 81) and z.shape == (8 * len(recs),)
+    game = OracleGame()
+    for k in range(0, len(recs), 5):
+        r = recs[k]
+        pos = GameState.from_packed(r["state"])
+        counts = r["counts"].astype(np.float64)
+        want_pi = counts / counts.sum() if r["tau_one"] else np.eye(81)[int(r["action"])]
+        syms = game.getSymmetries(pos, want_pi)
+        for j, (b, p) in enumerate(syms):
+            assert np.array_equal(obs[8 * k + j], np.asarray(b.get_obs()).reshape(4, 9, 9))
+            assert np.allclose(pi[8 * k + j], p.astype(np.float32))
+        want_z = float(r["z_sign"]) * (1e-4 if r["finished"] == 2 else 1.0)
+        assert np.allclose(z[8 * k:8 * k + 8], want_z)
+    ex = arrays_to_examples(obs, pi, z)
+    assert len(ex) == 8 * len(recs) and tuple(ex[0][0].shape) == (4, 9, 9) and tuple(ex[0][1].shape) == (81,)
+
+
+def test_selfplay_driver_generates_numenvs_games():
+    from tacult_b200.selfplay import SelfPlayDriver
+
+    class A(dict):
+        __getattr__ = dict.__getitem__
+
+    class HashNet:
+        tc_hash_params = (5, 0, 0)
+    drv = SelfPlayDriver(HashNet(), A(numEnvs=16, numMCTSSims=8, cpuct=2.4, tempThreshold=10))
+    recs, stats = drv.play_records(seed=3)
+    assert stats["games_finished"] == 16 and len(recs) == stats["plies"]      # exactly numEnvs games (coach.py:175)
+    assert sorted(set(recs["env"])) == list(range(16))
