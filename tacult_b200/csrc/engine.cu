@@ -73,8 +73,9 @@ struct tc_engine {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     TreeStore ts{};
-    DevBuf<uint4> node_hdr, path;
-    DevBuf<uint32_t> node_Ns, hash, eval_state, root_states, counts;
+    DevBuf<uint4> node_hdr;
+    DevBuf<uint2> path;
+    DevBuf<uint32_t> hash, eval_state, root_states, counts;
     DevBuf<unsigned long long> edge_mem, totals;
     DevBuf<TreeCtl> ctl;
     DevBuf<float> eval_pi, eval_v;
@@ -170,8 +171,7 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
         }                                                                                              \
     } while (0)
     TC_ALLOC(e->node_hdr, 2 * E * capN);
-    TC_ALLOC(e->node_Ns, E * capN);
-    TC_ALLOC(e->edge_mem, 3 * E * capE);
+    TC_ALLOC(e->edge_mem, 4 * E * capE);
     TC_ALLOC(e->hash, E * hs);
     TC_ALLOC(e->ctl, E);
     TC_ALLOC(e->path, E * MAX_DEPTH);
@@ -206,7 +206,6 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     ts.capE = (uint32_t)capE;
     ts.hashSize = (uint32_t)hs;
     ts.node_hdr = e->node_hdr.p;
-    ts.node_Ns = e->node_Ns.p;
     ts.edge_mem = e->edge_mem.p;
     ts.hash = e->hash.p;
     ts.ctl = e->ctl.p;

@@ -396,6 +396,53 @@ __global__ void __launch_bounds__(256) k_stem_bf16(int batch, const int *__restr
     }
 }
 
+// Observation planes as a 16-channel bf16 activation in the padded layout (channels >= in_planes are zero), so
+// that conv_in runs through the same tensor-core implicit GEMM as the trunk (K = 16 per tap).  One warp per position.
+__global__ void __launch_bounds__(256) k_encode_planes_bf16(int batch, const int *__restrict__ count_dev,
+                                                            const uint32_t *__restrict__ states,
+                                                            const float *__restrict__ obs, int in_planes,
+                                                            __nv_bfloat16 *__restrict__ out)
+{
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= live_count(count_dev, batch)) return;
+    Pos p;
+    uint32_t lw[3] = {0, 0, 0};
+    if (states) {
+        uint32_t wd[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wd[k] = states[8 * (size_t)row + k];
+        p = unpack(wd);
+        legal_words(p, summarize(p), lw);
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int a = lane + 32 * q;
+        if (a >= 81) continue;
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = 0.f;
+        if (states) {
+            const bool mine = action_bit(p.mine, a), occ = action_bit(p.occ, a);
+            v[0] = mine ? 1.f : 0.f;
+            v[1] = (occ && !mine) ? 1.f : 0.f;
+            v[2] = action_bit(lw, a) ? 1.f : 0.f;
+            v[3] = 1.f;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < in_planes) v[c] = obs[((size_t)row * in_planes + c) * 81 + a];
+        }
+        uint4 o[2];
+        __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(o);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) op[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+        uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)PAD0 + (size_t)row * ROWS_PER_POS + (a / 9) * 10 + a % 9) * 16);
+        dst[0] = o[0];
+        dst[1] = o[1];
+    }
+}
+
 // debug / test helper: padded or compact bf16 activations -> f32 [row][81][C]
 __global__ void k_unpad_to_f32(int batch, int C, const __nv_bfloat16 *__restrict__ in, int compact, float *__restrict__ out)
 {
@@ -458,6 +505,10 @@ struct NetBF16Impl {
     DevBuf<__nv_bfloat16> flat;            // compact [cap][81*C], fc1 input
     DevBuf<float> emb;                     // [cap][E]
     DevBuf<float> stem_w, stem_b;
+    DevBuf<__nv_bfloat16> planes;          // padded layout, 16 channels (observation planes, zero padded)
+    DevBuf<__nv_bfloat16> stem_w16;        // [9][C][16]
+    CUtensorMap map_planes, map_stem_w;
+    bool stem_on_tensor = false;
     std::vector<DevBuf<__nv_bfloat16>> conv_w;   // [9][Cout][Cin]
     std::vector<DevBuf<float>> conv_b;
     DevBuf<__nv_bfloat16> fc1_w;           // [E][81*C], k = p*C + c
@@ -547,6 +598,19 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
         TC_CUDA(cudaMemset(m.act[i].p, 0, m.act[i].bytes()));       // pad rows stay zero for ever
         TC_TRY(make_map(&m.map_act[i], m.act[i].p, m.act_rows, C, 128, (uint32_t)m.block_k));
     }
+    m.stem_on_tensor = I <= 16;
+    if (m.stem_on_tensor) {
+        std::vector<__nv_bfloat16> sw((size_t)9 * C * 16, __float2bfloat16_rn(0.f));
+        for (int tap = 0; tap < 9; ++tap)
+            for (int co = 0; co < C; ++co)
+                for (int ci = 0; ci < I; ++ci)
+                    sw[((size_t)tap * C + co) * 16 + ci] = __float2bfloat16_rn(f.stem_w[((size_t)co * I + ci) * 9 + tap]);
+        TC_TRY(upload(m.stem_w16, sw));
+        TC_CUDA(m.planes.alloc(m.act_rows * 16));
+        TC_CUDA(cudaMemset(m.planes.p, 0, m.planes.bytes()));
+        TC_TRY(make_map(&m.map_planes, m.planes.p, m.act_rows, 16, 128, 16));
+        TC_TRY(make_map(&m.map_stem_w, m.stem_w16.p, (uint64_t)9 * C, 16, (uint32_t)C, 16));
+    }
     const size_t flat_rows = std::max(cap, 128);
     TC_CUDA(m.flat.alloc(flat_rows * 81 * C));
     TC_CUDA(cudaMemset(m.flat.p, 0, m.flat.bytes()));
@@ -613,10 +677,34 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
     const int total = 2 * m.d.num_residual_blocks;
     const bool stem_flat = to_flat && n_convs == 0;
     prof->begin(TC_K_NN_STEM, st);
-    k_stem_bf16<<<batch, 256, sizeof(float) * I * 121, st>>>(batch, count_dev, states, obs, I, C, m.stem_w.p, m.stem_b.p,
-                                                             stem_flat ? m.flat.p : m.act[0].p, stem_flat ? 1 : 0);
+    if (m.stem_on_tensor) {
+        k_encode_planes_bf16<<<ceil_div(batch, 8), 256, 0, st>>>(batch, count_dev, states, obs, I, m.planes.p);
+        GemmParams S{};
+        S.count_dev = count_dev;
+        S.batch = batch;
+        S.rows_per_unit = ROWS_PER_POS;
+        S.taps = 9;
+        S.k_chunks = 1;
+        S.block_n = C;
+        S.n_blocks = 1;
+        S.a_row0 = PAD0;
+        S.b_tap_rows = C;
+        S.stages = pick_stages(16, C, 48 * 1024);
+        S.mode = stem_flat ? OUT_COMPACT_BF16 : OUT_PADDED_BF16;
+        S.relu = 1;
+        S.ldc = C;
+        S.bias = m.stem_b.p;
+        S.residual = nullptr;
+        S.out = stem_flat ? (void *)m.flat.p : (void *)m.act[0].p;
+        launch_gemm(m, 16, m.map_planes, m.map_stem_w, S, (batch * ROWS_PER_POS + 127) / 128, st);
+        launches += 2;
+    } else {
+        k_stem_bf16<<<batch, 256, sizeof(float) * I * 121, st>>>(batch, count_dev, states, obs, I, C, m.stem_w.p,
+                                                                 m.stem_b.p, stem_flat ? m.flat.p : m.act[0].p,
+                                                                 stem_flat ? 1 : 0);
+        ++launches;
+    }
     prof->end(st);
-    ++launches;
     if (stem_flat) return -1;
     int x = 0, y = 1, z = 2;
     const int max_tiles = ((batch * ROWS_PER_POS + 127) / 128);

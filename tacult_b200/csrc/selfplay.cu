@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(128) k_selfplay_move(TreeStore ts, SelfPlaySto
         lg[q] = (a < 81) && action_bit(lw, a);
         am[q] = __ballot_sync(FULL, lg[q]);
     }
-    const uint32_t *edgeN = reinterpret_cast<const uint32_t *>(
-        reinterpret_cast<const double *>(ts.edge_mem + 3ull * ((unsigned long long)env * ts.capE + off)) + 2 * n);
+    const uint32_t *edgeN = edge_block(ts, env, off, n).N;
     uint32_t cnt[3];
     uint32_t total = 0, maxc = 0;
 #pragma unroll

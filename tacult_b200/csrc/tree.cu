@@ -47,24 +47,6 @@ __device__ __forceinline__ int edge_index(const uint32_t am[3], int q, int lane)
     return j;
 }
 
-struct EdgeBlock {
-    double *P;
-    double *Q;
-    uint32_t *N;
-    uint32_t *child;
-};
-
-__device__ __forceinline__ EdgeBlock edge_block(const TreeStore &ts, int tree, uint32_t edge_off, uint32_t n)
-{
-    unsigned long long *base = ts.edge_mem + 3ull * ((unsigned long long)tree * ts.capE + edge_off);
-    EdgeBlock b;
-    b.P = reinterpret_cast<double *>(base);
-    b.Q = b.P + n;
-    b.N = reinterpret_cast<uint32_t *>(b.Q + n);
-    b.child = b.N + n;
-    return b;
-}
-
 // Looks the position up in the tree's table.  Returns the node index or -1; when absent `free_slot`
 // is where it would be inserted (0xFFFFFFFF if the table is full).
 __device__ int table_find(const TreeStore &ts, int tree, const Pos &p, uint64_t h, int lane, uint32_t &free_slot)
@@ -100,45 +82,58 @@ __device__ int table_find(const TreeStore &ts, int tree, const Pos &p, uint64_t 
     return -1;
 }
 
-// Creates a node for `p` (n legal moves, action mask am) and requests its evaluation.
-// Returns the node index, or -1 if a pool is exhausted (error flag raised, tree parked).
-__device__ int create_leaf(const TreeStore &ts, int tree, TreeCtl &c, const Pos &p, uint64_t h, uint32_t free_slot,
-                           const uint32_t am[3], int lane)
+// per-warp view of the mutable part of TreeCtl, kept in registers during k_select
+struct Walk {
+    uint32_t n_nodes, n_edges;
+    int active, leaf_kind, leaf_node, leaf_row;
+    double leaf_value;
+    uint32_t nn_leaves, sum_leaf_legal;
+};
+
+// Creates a node for `p` (action mask am) and requests its evaluation.  Returns the node index, or -1 if a
+// pool is exhausted (error flag raised, tree parked).  off/n receive the new node's edge block.
+__device__ int create_leaf(const TreeStore &ts, int tree, Walk &w, const Pos &p, uint64_t h, uint32_t free_slot,
+                           const uint32_t am[3], int lane, uint32_t &off, uint32_t &n)
 {
-    uint32_t n = (uint32_t)(__popc(am[0]) + __popc(am[1]) + __popc(am[2]));
-    if (c.n_nodes >= ts.capN || c.n_edges + n > ts.capE || free_slot == 0xFFFFFFFFu) {
+    n = (uint32_t)(__popc(am[0]) + __popc(am[1]) + __popc(am[2]));
+    if (w.n_nodes >= ts.capN || w.n_edges + n > ts.capE || free_slot == 0xFFFFFFFFu) {
         if (lane == 0) atomicExch(ts.error_flag, 1);
-        c.active = 0;
+        w.active = 0;
         return -1;
     }
-    uint32_t idx = c.n_nodes++;
-    uint32_t off = c.n_edges;
-    c.n_edges += n;
+    uint32_t idx = w.n_nodes++;
+    off = w.n_edges;
+    w.n_edges += n;
     size_t g = (size_t)tree * ts.capN + idx;
     if (lane == 0) {
         ts.node_hdr[2 * g] = make_uint4(p.mine[0], p.mine[1], p.mine[2], p.occ[0]);
         ts.node_hdr[2 * g + 1] = make_uint4(p.occ[1], p.occ[2], p.last | (n << 8), off);
-        ts.node_Ns[g] = 0u;
         ts.hash[(size_t)tree * ts.hashSize + free_slot] = (((uint32_t)(h >> 40) & 0xFFFu) << 20) | (idx + 1u);
     }
     EdgeBlock eb = edge_block(ts, tree, off, n);
-    for (uint32_t j = lane; j < n; j += 32) {
-        eb.N[j] = 0u;
-        eb.child[j] = CHILD_UNRESOLVED;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if ((am[q] >> lane) & 1u) {
+            int j = edge_index(am, q, lane);
+            eb.N[j] = 0u;
+            eb.child[j] = CHILD_UNRESOLVED;
+            eb.coff[j] = 0u;
+            eb.meta[j] = (uint32_t)(lane + 32 * q);
+        }
     }
     int row = 0;
     if (lane == 0) row = atomicAdd(ts.eval_count, 1);
     row = __shfl_sync(FULL, row, 0);
     if (lane < 8) {
-        uint32_t w = lane == 0 ? p.mine[0] : lane == 1 ? p.mine[1] : lane == 2 ? p.mine[2] : lane == 3 ? p.occ[0]
+        uint32_t v = lane == 0 ? p.mine[0] : lane == 1 ? p.mine[1] : lane == 2 ? p.mine[2] : lane == 3 ? p.occ[0]
                    : lane == 4 ? p.occ[1] : lane == 5 ? p.occ[2] : lane == 6 ? p.last : 0u;
-        ts.eval_state[8 * (size_t)row + lane] = w;
+        ts.eval_state[8 * (size_t)row + lane] = v;
     }
-    c.leaf_kind = LEAF_NN;
-    c.leaf_node = (int)idx;
-    c.leaf_row = row;
-    c.nn_leaves += 1;
-    c.sum_leaf_legal += n;
+    w.leaf_kind = LEAF_NN;
+    w.leaf_node = (int)idx;
+    w.leaf_row = row;
+    w.nn_leaves += 1;
+    w.sum_leaf_legal += n;
     return (int)idx;
 }
 
@@ -184,6 +179,8 @@ __global__ void k_reset(TreeStore ts, int env)
         c->leaf_row = 0;
         c->path_len = 0;
         c->leaf_value = 0.0;
+        c->root_off = 0;
+        c->root_n = 0;
     }
 }
 
@@ -200,7 +197,15 @@ __global__ void k_set_roots(TreeStore ts, const uint32_t *__restrict__ states, c
     bool on = (active == nullptr || active[tree] != 0) && status == 0;
     uint32_t free_slot;
     int idx = -1;
-    if (on) idx = table_find(ts, tree, p, key_hash(p), lane, free_slot);
+    uint32_t off = 0, n = 0;
+    if (on) {
+        idx = table_find(ts, tree, p, key_hash(p), lane, free_slot);
+        if (idx >= 0) {
+            const uint4 *hdr = ts.node_hdr + 2ull * ((size_t)tree * ts.capN + idx);
+            Pos q;
+            unpack_hdr(hdr[0], hdr[1], q, n, off);
+        }
+    }
     if (lane == 0) {
         TreeCtl *c = ts.ctl + tree;
         uint32_t packed[8];
@@ -208,146 +213,215 @@ __global__ void k_set_roots(TreeStore ts, const uint32_t *__restrict__ states, c
 #pragma unroll
         for (int k = 0; k < 8; ++k) c->root_state[k] = packed[k];
         c->root_idx = idx;
+        c->root_off = off;
+        c->root_n = n;
         c->active = on ? 1 : 0;
         c->leaf_kind = LEAF_NONE;
         c->path_len = 0;
     }
 }
 
+struct EdgeRegs {     // one edge as held by its lane during selection
+    double P, Q;
+    uint32_t N, child, coff, meta;
+};
+
 // One simulation's descent for every tree: mcts.py:243-325 (selection part of `_search`).
-__global__ void __launch_bounds__(128) k_select(TreeStore ts, double cpuct)
+// Every level costs one dependent memory round trip: the lanes load the whole edge block (priors, values,
+// counts and where each child lives), Ns is the warp sum of the counts, the arg-max lane broadcasts the child.
+__global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
 {
-    int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+    const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (tree >= ts.E) return;
-    TreeCtl c = ts.ctl[tree];
-    c.leaf_kind = LEAF_NONE;
-    c.path_len = 0;
-    if (!c.active) {
-        if (lane == 0) { ts.ctl[tree].leaf_kind = LEAF_NONE; ts.ctl[tree].path_len = 0; }
+    TreeCtl *cp = ts.ctl + tree;
+    Walk w;
+    w.active = cp->active;
+    if (!w.active) {
+        if (lane == 0) { cp->leaf_kind = LEAF_NONE; cp->path_len = 0; }
         return;
     }
-    c.sims += 1;
-    uint4 *path = ts.path + (size_t)tree * MAX_DEPTH;
+    w.n_nodes = cp->n_nodes;
+    w.n_edges = cp->n_edges;
+    w.leaf_kind = LEAF_NONE;
+    w.leaf_node = -1;
+    w.leaf_row = 0;
+    w.leaf_value = 0.0;
+    w.nn_leaves = 0;
+    w.sum_leaf_legal = 0;
+    int root_idx = cp->root_idx;
+    uint32_t root_off = cp->root_off, root_n = cp->root_n;
+    uint32_t depth = 0, sum_legal = 0, terminal = 0, transp = 0;
+    uint2 *path = ts.path + (size_t)tree * MAX_DEPTH;
     const uint4 *hdr = ts.node_hdr + 2ull * (size_t)tree * ts.capN;
-    const uint32_t *nodeNs = ts.node_Ns + (size_t)tree * ts.capN;
 
-    if (c.root_idx < 0) {
+    if (root_idx < 0) {
         // root never expanded: it is this simulation's leaf (mcts.py:268-290 at recursion depth 0)
-        Pos p = unpack(c.root_state);
+        uint32_t rs[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rs[k] = cp->root_state[k];
+        Pos p = unpack(rs);
         uint32_t am[3];
         int status;
         warp_legal_mask(p, lane, am, status);
         uint64_t h = key_hash(p);
         uint32_t free_slot;
         int idx = table_find(ts, tree, p, h, lane, free_slot);
-        if (idx < 0) idx = create_leaf(ts, tree, c, p, h, free_slot, am, lane);
-        c.root_idx = idx;
+        if (idx < 0) idx = create_leaf(ts, tree, w, p, h, free_slot, am, lane, root_off, root_n);
+        root_idx = idx;
     } else {
-        int cur = c.root_idx;
-        int depth = 0;
+        int cur = root_idx;
+        uint32_t off = root_off, n = root_n;
         while (true) {
-            uint4 h0 = hdr[2ull * cur], h1 = hdr[2ull * cur + 1];
-            Pos p;
-            uint32_t n, off;
-            unpack_hdr(h0, h1, p, n, off);
-            uint32_t ns = nodeNs[cur];
-            uint32_t am[3];
-            int status;
-            warp_legal_mask(p, lane, am, status);
             EdgeBlock eb = edge_block(ts, tree, off, n);
-
-            // PUCT over the legal edges (mcts.py:301-316); lane l scores actions l, l+32, l+64
-            const double sq_visited = __dsqrt_rn((double)ns);
-            const double sq_fresh = __dsqrt_rn(__dadd_rn((double)ns, 1e-8));
-            double best_u = -INFINITY;
-            int best_a = 1 << 20, best_j = -1;
-            double pj[3], qj[3];
-            uint32_t nj[3];
-            int jj[3];
+            EdgeRegs e[3];
+            uint32_t nsum = 0;
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                jj[q] = -1;
-                if ((am[q] >> lane) & 1u) {
-                    int j = edge_index(am, q, lane);
-                    jj[q] = j;
-                    pj[q] = eb.P[j];
-                    qj[q] = eb.Q[j];
-                    nj[q] = eb.N[j];
+                const uint32_t j = (uint32_t)lane + 32u * q;
+                e[q].N = 0;
+                if (j < n) {
+                    e[q].P = eb.P[j];
+                    e[q].Q = eb.Q[j];
+                    e[q].N = eb.N[j];
+                    e[q].child = eb.child[j];
+                    e[q].coff = eb.coff[j];
+                    e[q].meta = eb.meta[j];
+                    nsum += e[q].N;
                 }
             }
 #pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) nsum += __shfl_xor_sync(FULL, nsum, d);     // Ns[s]
+
+            // PUCT over the legal edges (mcts.py:301-316)
+            const double sq_visited = __dsqrt_rn((double)nsum);
+            const double sq_fresh = __dsqrt_rn(__dadd_rn((double)nsum, 1e-8));
+            double best_u = -INFINITY;
+            int best_j = 1 << 20;
+#pragma unroll
             for (int q = 0; q < 3; ++q) {
-                if (jj[q] >= 0) {
-                    double cp = __dmul_rn(cpuct, pj[q]);
-                    double u = nj[q] ? __dadd_rn(qj[q], __ddiv_rn(__dmul_rn(cp, sq_visited), (double)(1u + nj[q])))
-                                     : __dmul_rn(cp, sq_fresh);
-                    if (u > best_u) { best_u = u; best_a = lane + 32 * q; best_j = jj[q]; }
+                const uint32_t j = (uint32_t)lane + 32u * q;
+                if (j < n) {
+                    double cpp = __dmul_rn(cpuct, e[q].P);
+                    double u = e[q].N ? __dadd_rn(e[q].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[q].N)))
+                                      : __dmul_rn(cpp, sq_fresh);
+                    if (u > best_u) { best_u = u; best_j = (int)j; }       // ascending j: first maximum wins
                 }
             }
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
                 double ou = __shfl_xor_sync(FULL, best_u, d);
-                int oa = __shfl_xor_sync(FULL, best_a, d);
                 int oj = __shfl_xor_sync(FULL, best_j, d);
-                // a lane that found nothing carries best_j == -1 and never wins
-                bool take = (oj >= 0) && (best_j < 0 || ou > best_u || (ou == best_u && oa < best_a));
-                if (take) { best_u = ou; best_a = oa; best_j = oj; }
+                // edges are in action order, so "lowest action index wins ties" (strict '>' in mcts.py:314) is
+                // "lowest j wins"; a lane that found nothing carries j = 2^20 and never wins
+                if (oj < (1 << 20) && (best_j >= (1 << 20) || ou > best_u || (ou == best_u && oj < best_j))) {
+                    best_u = ou;
+                    best_j = oj;
+                }
             }
-            c.sum_depth += 1;
-            c.sum_legal += n;
-            if (best_j < 0) {           // cannot happen for a live position; park the tree loudly
+            sum_legal += n;
+            if (best_j >= (1 << 20)) {       // cannot happen for a live position; park the tree loudly
                 if (lane == 0) atomicExch(ts.error_flag, 2);
-                c.active = 0;
-                c.path_len = 0;
+                w.active = 0;
+                depth = 0;
                 break;
             }
-            if (lane == 0) path[depth] = make_uint4((uint32_t)cur, off, (uint32_t)best_j | (n << 8), (uint32_t)best_a);
+            if (lane == 0) path[depth] = make_uint2(off, (uint32_t)best_j | (n << 8));
             ++depth;
-            c.path_len = depth;
 
-            uint32_t child = eb.child[best_j];
+            // the winning lane broadcasts where the child lives
+            const int wq = best_j >> 5, wl = best_j & 31;
+            uint32_t child = wq == 0 ? e[0].child : (wq == 1 ? e[1].child : e[2].child);
+            uint32_t coff = wq == 0 ? e[0].coff : (wq == 1 ? e[1].coff : e[2].coff);
+            uint32_t meta = wq == 0 ? e[0].meta : (wq == 1 ? e[1].meta : e[2].meta);
+            child = __shfl_sync(FULL, child, wl);
+            coff = __shfl_sync(FULL, coff, wl);
+            meta = __shfl_sync(FULL, meta, wl);
+
             if (child >= CHILD_TERM_BASE && child != CHILD_UNRESOLVED) {
                 int st = (int)(child - CHILD_TERM_BASE);
-                c.leaf_kind = LEAF_TERMINAL;
-                c.leaf_value = st == 2 ? 1e-4 : (st == 3 ? 1.0 : -1.0);   // utac_game.py:64-81
-                c.terminal_leaves += 1;
+                w.leaf_kind = LEAF_TERMINAL;
+                w.leaf_value = st == 2 ? 1e-4 : (st == 3 ? 1.0 : -1.0);   // utac_game.py:64-81
+                terminal += 1;
                 break;
             }
-            if (child != CHILD_UNRESOLVED) { cur = (int)child; continue; }
+            if (child != CHILD_UNRESOLVED) {
+                cur = (int)child;
+                off = coff;
+                n = (meta >> 8) & 0xFFu;
+                continue;
+            }
 
             // first traversal of this edge: successor position (mcts.py:319-320)
-            Pos nx = play(p, best_a);
+            uint4 h0 = hdr[2ull * cur], h1 = hdr[2ull * cur + 1];
+            Pos p;
+            uint32_t pn, poff;
+            unpack_hdr(h0, h1, p, pn, poff);
+            const int action = (int)(meta & 0xFFu);
+            Pos nx = play(p, action);
             uint32_t nam[3];
             int nst;
             warp_legal_mask(nx, lane, nam, nst);
             if (nst != 0) {
                 if (lane == 0) eb.child[best_j] = CHILD_TERM_BASE + (uint32_t)nst;
-                c.leaf_kind = LEAF_TERMINAL;
-                c.leaf_value = nst == 2 ? 1e-4 : (nst == 3 ? 1.0 : -1.0);
-                c.terminal_leaves += 1;
+                w.leaf_kind = LEAF_TERMINAL;
+                w.leaf_value = nst == 2 ? 1e-4 : (nst == 3 ? 1.0 : -1.0);
+                terminal += 1;
                 break;
             }
             uint64_t h = key_hash(nx);
             uint32_t free_slot;
             int idx = table_find(ts, tree, nx, h, lane, free_slot);
             if (idx >= 0) {             // transposition: the position is already a node (mcts.py:268 is false)
-                if (lane == 0) eb.child[best_j] = (uint32_t)idx;
-                c.transpositions += 1;
+                Pos q;
+                uint32_t cn, co;
+                unpack_hdr(hdr[2ull * idx], hdr[2ull * idx + 1], q, cn, co);
+                if (lane == 0) {
+                    eb.child[best_j] = (uint32_t)idx;
+                    eb.coff[best_j] = co;
+                    eb.meta[best_j] = (uint32_t)action | (cn << 8);
+                }
+                transp += 1;
                 cur = idx;
+                off = co;
+                n = cn;
                 continue;
             }
-            idx = create_leaf(ts, tree, c, nx, h, free_slot, nam, lane);
+            uint32_t co = 0, cn = 0;
+            idx = create_leaf(ts, tree, w, nx, h, free_slot, nam, lane, co, cn);
             if (idx >= 0) {
-                if (lane == 0) eb.child[best_j] = (uint32_t)idx;
+                if (lane == 0) {
+                    eb.child[best_j] = (uint32_t)idx;
+                    eb.coff[best_j] = co;
+                    eb.meta[best_j] = (uint32_t)action | (cn << 8);
+                }
             } else {
-                c.path_len = 0;         // pool exhausted: drop this simulation
-                c.leaf_kind = LEAF_NONE;
+                depth = 0;              // pool exhausted: drop this simulation
+                w.leaf_kind = LEAF_NONE;
             }
             break;
         }
     }
-    if (lane == 0) ts.ctl[tree] = c;
+    if (lane == 0) {
+        cp->root_idx = root_idx;
+        cp->root_off = root_off;
+        cp->root_n = root_n;
+        cp->active = w.active;
+        cp->n_nodes = w.n_nodes;
+        cp->n_edges = w.n_edges;
+        cp->leaf_kind = w.leaf_kind;
+        cp->leaf_node = w.leaf_node;
+        cp->leaf_row = w.leaf_row;
+        cp->leaf_value = w.leaf_value;
+        cp->path_len = (int)depth;
+        cp->sims += 1;
+        cp->sum_depth += depth;
+        cp->sum_legal += sum_legal;
+        cp->nn_leaves += w.nn_leaves;
+        cp->sum_leaf_legal += w.sum_leaf_legal;
+        cp->terminal_leaves += terminal;
+        cp->transpositions += transp;
+    }
 }
 
 // numpy's float64 np.sum over 81 contiguous values (8 running sums, pairwise tree, tail), mcts.py:273
@@ -414,21 +488,19 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
         x = cp->leaf_value;
     }
     // edge `dist` levels above the leaf receives 0.0 + -(value one level below)  (mcts.py:325,342)
-    const uint4 *path = ts.path + (size_t)tree * MAX_DEPTH;
-    uint32_t *nodeNs = ts.node_Ns + (size_t)tree * ts.capN;
+    const uint2 *path = ts.path + (size_t)tree * MAX_DEPTH;
     for (int e = lane; e < path_len; e += 32) {
-        uint4 pe = path[e];
+        uint2 pe = path[e];
         int dist = path_len - e;
         double v = (dist & 1) ? -x : x;
         v = __dadd_rn(0.0, v);                                  // -0.0 normalises to +0.0 as in the reference
-        uint32_t n = pe.z >> 8, j = pe.z & 0xFFu;
-        EdgeBlock eb = edge_block(ts, tree, pe.y, n);
+        uint32_t n = pe.y >> 8, j = pe.y & 0xFFu;
+        EdgeBlock eb = edge_block(ts, tree, pe.x, n);
         uint32_t cnt = eb.N[j];
         double q = v;
         if (cnt) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)cnt, eb.Q[j]), v), (double)(cnt + 1u));
         eb.Q[j] = q;
         eb.N[j] = cnt + 1u;
-        nodeNs[pe.x] += 1u;
     }
 }
 

@@ -12,11 +12,13 @@
 //     (__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn: no FMA contraction).
 //
 // Layout in HBM (one warp owns one tree, so nothing below needs atomics):
-//   node header  32 B : mine[3] occ[3] meta(last_square+1 | n_edges<<8) edge_off   — immutable
-//   node Ns       4 B : separate array (the only mutable per-node word)
-//   edge block  24n B : P[n] f64 | Q[n] f64 | N[n] u32 | child[n] u32, edges in action order;
-//                       the action of edge j is the j-th set bit of the node's legal mask,
-//                       so it is recomputed from the header instead of stored
+//   node header  32 B : mine[3] occ[3] meta(last_square+1 | n_edges<<8) edge_off   — immutable; only read when
+//                       a node is expanded or looked up, never on the way down
+//   edge block  32n B : P[n] f64 | Q[n] f64 | N[n] u32 | child[n] u32 | coff[n] u32 | meta[n] u32, edges in
+//                       action order.  meta = action | n_edges(child)<<8, coff = edge block of the child: an edge
+//                       carries everything needed to step to the child's edge block, so one level of the descent
+//                       is ONE dependent memory round trip.  Ns[s] is not stored: it always equals the sum of the
+//                       node's edge counts (both are incremented together, mcts.py:333-340).
 //   hash table   4 B/slot, per tree, open addressing, entry = tag(12) | node index + 1 (20)
 #pragma once
 #include "common.cuh"
@@ -43,6 +45,8 @@ struct TreeCtl {
     int32_t leaf_row;
     int32_t path_len;
     double leaf_value;       // value of a terminal leaf seen by its side to move (mcts.py:254-258)
+    uint32_t root_off;       // edge block of the root
+    uint32_t root_n;
     // counters
     unsigned long long sims, sum_depth, sum_legal, nn_leaves, sum_leaf_legal, terminal_leaves, transpositions;
 };
@@ -51,17 +55,40 @@ struct TreeStore {
     int E;
     uint32_t capN, capE, hashSize;
     uint4 *node_hdr;
-    uint32_t *node_Ns;
-    unsigned long long *edge_mem;
+    unsigned long long *edge_mem;   // [E][capE][4]: 32 bytes per edge
     uint32_t *hash;
     TreeCtl *ctl;
-    uint4 *path;
+    uint2 *path;                    // [E][MAX_DEPTH]: (edge_off, slot | n<<8)
     uint32_t *eval_state;    // [E][8]  leaves to evaluate, compacted
     float *eval_pi;          // [E][81]
     float *eval_v;           // [E]
     int *eval_count;
     int *error_flag;
 };
+
+struct EdgeBlock {
+    double *P;
+    double *Q;
+    uint32_t *N;
+    uint32_t *child;
+    uint32_t *coff;
+    uint32_t *meta;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ EdgeBlock edge_block(const TreeStore &ts, int tree, uint32_t edge_off, uint32_t n)
+{
+    unsigned long long *base = ts.edge_mem + 4ull * ((unsigned long long)tree * ts.capE + edge_off);
+    EdgeBlock b;
+    b.P = reinterpret_cast<double *>(base);
+    b.Q = b.P + n;
+    b.N = reinterpret_cast<uint32_t *>(b.Q + n);
+    b.child = b.N + n;
+    b.coff = b.child + n;
+    b.meta = b.coff + n;
+    return b;
+}
+#endif
 
 struct HashEvalParams {
     unsigned long long salt;
