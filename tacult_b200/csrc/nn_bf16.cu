@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "nn_bf16.cuh"
 #include "rules.cuh"
@@ -29,6 +30,8 @@ constexpr int PAD0 = 16;            // zero rows in front of position 0 (>= 11, 
 constexpr int ROWS_PER_POS = 100;
 constexpr int GEMM_THREADS = 192;
 constexpr int MAX_STAGES = 8;
+constexpr int SH_ROWS = 160;        // shifted variant: rows [g0-16, g0+144) of the activation per 128-row tile
+constexpr int SH_LEAD = 16;
 
 enum { OUT_PADDED_BF16 = 0, OUT_COMPACT_BF16 = 1, OUT_F32 = 2 };
 
@@ -43,6 +46,7 @@ struct GemmParams {
     int a_row0;               // first A row of GEMM row 0 (PAD0 for conv, 0 for fc1)
     int b_tap_rows;           // rows of the weight tensor per tap
     int stages;
+    int variant;              // 0: one TMA box per tap; 1/2: ONE box per tile + 9 shifted UMMA descriptors (conv, K<=64)
     int mode;
     int relu;
     int ldc;                  // output row length in elements (C or E)
@@ -187,10 +191,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = (P.block_n * SW + 1023) & ~1023;
-    const int stage_bytes = A_BYTES + b_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)P.stages * stage_bytes);
+    const bool shifted = P.variant != 0;
+    // classic: stages x [A 128 rows | B]; shifted: [9 weight taps, resident] then stages x [A 160 rows]
+    const int stage_bytes = shifted ? SH_ROWS * SW : A_BYTES + b_bytes;
+    const int w_bytes = shifted ? 9 * b_bytes : 0;
+    uint8_t *stage0 = smem + w_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage0 + (size_t)P.stages * stage_bytes);
     uint64_t *full = bars, *empty = bars + MAX_STAGES, *tfull = bars + 2 * MAX_STAGES, *tempty = bars + 2 * MAX_STAGES + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
+    uint64_t *wbar = bars + 2 * MAX_STAGES + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int count = live_count(P.count_dev, P.batch);
@@ -204,6 +213,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        mbar_init(wbar, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -216,7 +226,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (lane == 0 && shifted) {
+            // weights of all 9 taps once per CTA, then one activation box (with halo rows) per tile
+            if ((int)blockIdx.x < n_tiles) {
+                mbar_expect_tx(wbar, (uint32_t)(9 * P.block_n * SW));
+                for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem + tap * b_bytes, &tmB, wbar, 0, tap * P.b_tap_rows);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(empty + stage, phase ^ 1u);
+                mbar_expect_tx(full + stage, (uint32_t)(SH_ROWS * SW));
+                tma_load_2d(stage0 + (size_t)stage * stage_bytes, &tmA, full + stage, 0, P.a_row0 + 128 * tile - SH_LEAD);
+                if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+            }
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -226,7 +250,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
                     const int tap = kb / P.k_chunks, kc = kb - tap * P.k_chunks;
                     const int shift = P.taps == 9 ? (tap / 3 - 1) * 10 + (tap % 3 - 1) : 0;
                     mbar_wait(empty + stage, phase ^ 1u);
-                    uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t *sa = stage0 + (size_t)stage * stage_bytes;
                     mbar_expect_tx(full + stage, (uint32_t)(A_BYTES + P.block_n * SW));
                     tma_load_2d(sa, &tmA, full + stage, kc * BLOCK_K, a_row + shift);
                     tma_load_2d(sa + A_BYTES, &tmB, full + stage, kc * BLOCK_K, tap * P.b_tap_rows + nb * P.block_n);
@@ -236,7 +260,37 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (lane == 0 && shifted) {
+            const uint32_t idesc = make_instr_desc(P.block_n);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            if ((int)blockIdx.x < n_tiles) mbar_wait(wbar, 0);
+            const uint32_t w_addr = smem_u32(smem);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty + as, aphase ^ 1u);
+                mbar_wait(full + stage, phase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.block_n);
+                const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    // tap (dy,dx) = the same tile, 10*dy+dx rows further down: only the descriptor start moves
+                    const int shift = SH_LEAD + (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                    const uint32_t a_addr = a_base + (uint32_t)(shift * SW);
+                    const uint32_t b_addr = w_addr + (uint32_t)(tap * b_bytes);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        uint64_t adesc = make_smem_desc<SW>(a_addr + 32 * k);
+                        if (P.variant == 2) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;     // matrix base offset
+                        umma_bf16(d_tmem, adesc, make_smem_desc<SW>(b_addr + 32 * k), idesc, (uint32_t)((tap | k) != 0));
+                    }
+                }
+                umma_commit(empty + stage);
+                umma_commit(tfull + as);
+                if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        } else if (lane == 0) {
             const uint32_t idesc = make_instr_desc(P.block_n);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
@@ -247,7 +301,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k)
@@ -514,6 +568,8 @@ struct NetBF16Impl {
     DevBuf<__nv_bfloat16> fc1_w;           // [E][81*C], k = p*C + c
     DevBuf<float> fc1_b, head_w, head_b;
     CUtensorMap map_act[3], map_flat, map_fc1;
+    CUtensorMap map_act_sh[3], map_planes_sh;      // 160-row boxes for the shifted-descriptor variant
+    int conv_variant = 0;
     std::vector<CUtensorMap> map_conv_w;
     int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
     int sm_count = SM_COUNT;
@@ -521,16 +577,17 @@ struct NetBF16Impl {
 
 NetBF16::~NetBF16() { delete impl; }
 
-static size_t gemm_smem_bytes(int block_k, int block_n, int stages)
+static size_t gemm_smem_bytes(int block_k, int block_n, int stages, int variant = 0)
 {
     size_t a = 128 * block_k * 2, b = ((size_t)block_n * block_k * 2 + 1023) & ~(size_t)1023;
-    return 1024 + stages * (a + b) + (2 * MAX_STAGES + 4) * 8 + 16;
+    if (variant != 0) return 1024 + 9 * b + (size_t)stages * SH_ROWS * block_k * 2 + (2 * MAX_STAGES + 6) * 8 + 16;
+    return 1024 + stages * (a + b) + (2 * MAX_STAGES + 6) * 8 + 16;
 }
 
-static int pick_stages(int block_k, int block_n, size_t budget)
+static int pick_stages(int block_k, int block_n, size_t budget, int variant = 0)
 {
     int s = MAX_STAGES;
-    while (s > 2 && gemm_smem_bytes(block_k, block_n, s) > budget) --s;
+    while (s > 2 && gemm_smem_bytes(block_k, block_n, s, variant) > budget) --s;
     return s;
 }
 
@@ -548,6 +605,9 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     m.capacity = cap;
     const int C = f.d.channels, E = f.d.embedding_size, I = f.d.in_planes;
     m.block_k = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+    const char *var = getenv("TACULT_CONV_VARIANT");
+    m.conv_variant = var ? atoi(var) : 0;
+    if (C > 64) m.conv_variant = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m.sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -597,6 +657,7 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
         TC_CUDA(m.act[i].alloc(m.act_rows * C));
         TC_CUDA(cudaMemset(m.act[i].p, 0, m.act[i].bytes()));       // pad rows stay zero for ever
         TC_TRY(make_map(&m.map_act[i], m.act[i].p, m.act_rows, C, 128, (uint32_t)m.block_k));
+        if (C <= 64) TC_TRY(make_map(&m.map_act_sh[i], m.act[i].p, m.act_rows, C, SH_ROWS, (uint32_t)m.block_k));
     }
     m.stem_on_tensor = I <= 16;
     if (m.stem_on_tensor) {
@@ -609,6 +670,7 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
         TC_CUDA(m.planes.alloc(m.act_rows * 16));
         TC_CUDA(cudaMemset(m.planes.p, 0, m.planes.bytes()));
         TC_TRY(make_map(&m.map_planes, m.planes.p, m.act_rows, 16, 128, 16));
+        TC_TRY(make_map(&m.map_planes_sh, m.planes.p, m.act_rows, 16, SH_ROWS, 16));
         TC_TRY(make_map(&m.map_stem_w, m.stem_w16.p, (uint64_t)9 * C, 16, (uint32_t)C, 16));
     }
     const size_t flat_rows = std::max(cap, 128);
@@ -652,7 +714,7 @@ int NetBF16::upload(const FoldedNet &f, int capacity)
 static void launch_gemm(const NetBF16Impl &m, int block_k, const CUtensorMap &a, const CUtensorMap &b, const GemmParams &P,
                         int max_tiles, cudaStream_t st)
 {
-    const size_t smem = gemm_smem_bytes(block_k, P.block_n, P.stages);
+    const size_t smem = gemm_smem_bytes(block_k, P.block_n, P.stages, P.variant);
     int tmem_cols = 32;
     while (tmem_cols < 2 * P.block_n) tmem_cols <<= 1;
     int per_sm = (int)std::min<size_t>(4, (220 * 1024) / smem);
@@ -689,14 +751,15 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
         S.n_blocks = 1;
         S.a_row0 = PAD0;
         S.b_tap_rows = C;
-        S.stages = pick_stages(16, C, 48 * 1024);
+        S.variant = m.conv_variant;
+        S.stages = pick_stages(16, C, 48 * 1024, S.variant);
         S.mode = stem_flat ? OUT_COMPACT_BF16 : OUT_PADDED_BF16;
         S.relu = 1;
         S.ldc = C;
         S.bias = m.stem_b.p;
         S.residual = nullptr;
         S.out = stem_flat ? (void *)m.flat.p : (void *)m.act[0].p;
-        launch_gemm(m, 16, m.map_planes, m.map_stem_w, S, (batch * ROWS_PER_POS + 127) / 128, st);
+        launch_gemm(m, 16, S.variant ? m.map_planes_sh : m.map_planes, m.map_stem_w, S, (batch * ROWS_PER_POS + 127) / 128, st);
         launches += 2;
     } else {
         k_stem_bf16<<<batch, 256, sizeof(float) * I * 121, st>>>(batch, count_dev, states, obs, I, C, m.stem_w.p,
@@ -722,7 +785,8 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
         P.n_blocks = 1;
         P.a_row0 = PAD0;
         P.b_tap_rows = C;
-        P.stages = m.conv_stages;
+        P.variant = m.conv_variant;
+        P.stages = P.variant ? pick_stages(m.block_k, C, 64 * 1024, P.variant) : m.conv_stages;
         P.mode = last ? OUT_COMPACT_BF16 : OUT_PADDED_BF16;
         P.relu = 1;
         P.ldc = C;
@@ -732,7 +796,7 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
         P.residual = second ? m.act[x].p : nullptr;
         P.out = last ? (void *)m.flat.p : (void *)m.act[dst].p;
         prof->begin(TC_K_NN_CONV, st);
-        launch_gemm(m, m.block_k, m.map_act[src], m.map_conv_w[l], P, max_tiles, st);
+        launch_gemm(m, m.block_k, P.variant ? m.map_act_sh[src] : m.map_act[src], m.map_conv_w[l], P, max_tiles, st);
         prof->end(st);
         ++launches;
         cur = dst;
