@@ -606,8 +606,8 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     const int C = f.d.channels, E = f.d.embedding_size, I = f.d.in_planes;
     m.block_k = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
     const char *var = getenv("TACULT_CONV_VARIANT");
-    m.conv_variant = var ? atoi(var) : 0;
-    if (C > 64) m.conv_variant = 0;
+    m.conv_variant = var ? atoi(var) : 1;      // measured on B200: variant 1 is exact, variant 2 (base offset) is wrong
+    if (C > 64) m.conv_variant = 0;            // weights of all taps must fit in shared memory
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m.sm_count, cudaDevAttrMultiProcessorCount, dev);
