@@ -22,7 +22,9 @@
 #include <cstdlib>
 
 #include "nn_bf16.cuh"
+#include "nn_fused.cuh"
 #include "rules.cuh"
+#include "tcgen05.cuh"
 
 namespace tc {
 
@@ -54,123 +56,6 @@ struct GemmParams {
     const __nv_bfloat16 *residual;   // padded layout, may be null
     void *out;
 };
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers (sm_100a)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void fence_barrier_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand tile in shared memory, rows of SW bytes (= BLOCK_K bf16), SW-byte swizzle as written by TMA.
-// Fields: start address >> 4 [0,14), LBO [16,30) unused for one swizzle atom along K, SBO = 8 rows * SW [32,46),
-// version 1 [46,48), layout type [61,64): 2 = 128B, 4 = 64B, 6 = 32B swizzle.
-template <int SW>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
-{
-    constexpr uint64_t layout = SW == 128 ? 2ull : (SW == 64 ? 4ull : 6ull);
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((8u * SW) >> 4) << 32;
-    d |= 1ull << 46;
-    d |= layout << 61;
-    return d;
-}
-
-// kind::f16 instruction descriptor: D = f32 [4,6)=1, A = B = bf16 [7,10)=[10,13)=1, both K-major, N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t make_instr_desc(int n)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
 
 __device__ __forceinline__ int live_count(const int *count_dev, int batch)
 {
@@ -570,6 +455,12 @@ struct NetBF16Impl {
     CUtensorMap map_act[3], map_flat, map_fc1;
     CUtensorMap map_act_sh[3], map_planes_sh;      // 160-row boxes for the shifted-descriptor variant
     int conv_variant = 0;
+    // fused shared-memory-resident trunk (C <= 64)
+    bool fused = false;
+    int fused_G = 0, fused_T = 0;
+    DevBuf<__nv_bfloat16> conv_w_all;      // [n_conv][9][C][C]
+    DevBuf<float> bias_all;                // [1 + n_conv][C]
+    CUtensorMap map_conv_w_all;
     std::vector<CUtensorMap> map_conv_w;
     int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
     int sm_count = SM_COUNT;
@@ -681,6 +572,32 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     TC_TRY(make_map(&m.map_flat, m.flat.p, (uint64_t)flat_rows, (uint64_t)81 * C, 128, 64));
     TC_TRY(make_map(&m.map_fc1, m.fc1_w.p, (uint64_t)E, (uint64_t)81 * C, (uint32_t)m.fc1_block_n, 64));
 
+    {
+        const char *fz = getenv("TACULT_FUSED");
+        int G = 0, T = 0;
+        m.fused = m.stem_on_tensor && (!fz || atoi(fz) != 0) && fused_plan(C, G, T);
+        if (m.fused) {
+            // balance the persistent grid: as few groups per CTA as the capacity needs, all of about the same size
+            const int waves = (cap + m.sm_count * G - 1) / (m.sm_count * G);
+            const int g_bal = (cap + m.sm_count * waves - 1) / (m.sm_count * waves);
+            m.fused_G = std::max(1, std::min(G, g_bal));
+            m.fused_T = (100 * m.fused_G + 127) / 128;
+            std::vector<__nv_bfloat16> wall(std::max<size_t>(1, L) * 9 * C * C);
+            std::vector<float> ball((1 + L) * (size_t)C);
+            for (int c = 0; c < C; ++c) ball[c] = f.stem_b[c];
+            for (size_t l = 0; l < L; ++l) {
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int co = 0; co < C; ++co)
+                        for (int ci = 0; ci < C; ++ci)
+                            wall[((l * 9 + tap) * C + co) * C + ci] =
+                                __float2bfloat16_rn(f.conv_w[l][((size_t)co * C + ci) * 9 + tap]);
+                for (int c = 0; c < C; ++c) ball[(1 + l) * C + c] = f.conv_b[l][c];
+            }
+            TC_TRY(upload(m.conv_w_all, wall));
+            TC_TRY(upload(m.bias_all, ball));
+            TC_TRY(make_map(&m.map_conv_w_all, m.conv_w_all.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)C, (uint32_t)C));
+        }
+    }
     const size_t budget = 200 * 1024;
     m.conv_stages = pick_stages(m.block_k, C, C <= 64 ? 48 * 1024 : budget);
     m.fc1_stages = pick_stages(64, m.fc1_block_n, 96 * 1024);
@@ -737,6 +654,14 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
 {
     const int C = m.d.channels, I = m.d.in_planes;
     const int total = 2 * m.d.num_residual_blocks;
+    if (m.fused && to_flat && n_convs >= total) {
+        prof->begin(TC_K_NN_CONV, st);
+        launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.fused_G, m.fused_T, total, I, batch, count_dev, states, obs,
+                           m.bias_all.p, m.flat.p, m.sm_count, st);
+        prof->end(st);
+        ++launches;
+        return -1;
+    }
     const bool stem_flat = to_flat && n_convs == 0;
     prof->begin(TC_K_NN_STEM, st);
     if (m.stem_on_tensor) {

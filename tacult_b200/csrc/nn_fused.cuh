@@ -1,0 +1,16 @@
+// Fused shared-memory-resident trunk for narrow nets; see nn_fused.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace tc {
+
+// largest tile count T (and positions per group G) that fits shared memory and TMEM for C channels
+bool fused_plan(int C, int &G, int &T);
+int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_conv, int G, int T, int n_conv,
+                       int in_planes, int batch, const int *count_dev, const uint32_t *states, const float *obs,
+                       const float *bias_all, __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st);
+
+}  // namespace tc
