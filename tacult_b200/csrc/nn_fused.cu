@@ -166,24 +166,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                     mbar_wait(wfull, ph);
                     tc_fence_after();
                     const uint32_t s_addr = smem_u32(src), w_addr = smem_u32(W);
-                    for (int t = 0; t < P.T; ++t) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(t * C);
+                    // Consecutive UMMAs into the SAME accumulator serialise on the tensor pipe's latency (N = C is a
+                    // few cycles of work each), so the issue order interleaves the tiles of a chunk: tap-major,
+                    // tile-minor.  Two chunks per layer let the epilogue of the first overlap the MMAs of the second.
+                    const int half = (P.T + 1) / 2;
+                    for (int t0 = 0; t0 < P.T; t0 += half) {
+                        const int t1 = min(P.T, t0 + half);
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
-                            const int shift = LEAD + 128 * t + (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                            const int shift0 = LEAD + (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             if (l == 0) {
-                                umma_bf16(d_tmem, make_smem_desc<SW>(s_addr + (uint32_t)(shift * SW)),
-                                          make_smem_desc<32>(w_addr + (uint32_t)(tap * WS_TAP)), idesc, (uint32_t)(tap != 0));
+                                const uint64_t bdesc = make_smem_desc<32>(w_addr + (uint32_t)(tap * WS_TAP));
+                                for (int t = t0; t < t1; ++t)
+                                    umma_bf16(tmem_base + (uint32_t)(t * C),
+                                              make_smem_desc<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW)), bdesc, idesc,
+                                              (uint32_t)(tap != 0));
                             } else {
-                                const uint32_t a_addr = s_addr + (uint32_t)(shift * SW);
-                                const uint32_t b_addr = w_addr + (uint32_t)(tap * W_TAP);
 #pragma unroll
-                                for (int k = 0; k < C / 16; ++k)
-                                    umma_bf16(d_tmem, make_smem_desc<SW>(a_addr + 32 * k), make_smem_desc<SW>(b_addr + 32 * k),
-                                              idesc, (uint32_t)((tap | k) != 0));
+                                for (int k = 0; k < C / 16; ++k) {
+                                    const uint64_t bdesc = make_smem_desc<SW>(w_addr + (uint32_t)(tap * W_TAP) + 32 * k);
+                                    for (int t = t0; t < t1; ++t)
+                                        umma_bf16(tmem_base + (uint32_t)(t * C),
+                                                  make_smem_desc<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW) + 32 * k), bdesc,
+                                                  idesc, (uint32_t)((tap | k) != 0));
+                                }
                             }
                         }
-                        umma_commit(tdone + t);
+                        for (int t = t0; t < t1; ++t) umma_commit(tdone + t);
                     }
                     umma_commit(wfree);
                 }
