@@ -459,8 +459,8 @@ struct NetBF16Impl {
     bool fused = false;
     int fused_G = 0, fused_T = 0;
     DevBuf<__nv_bfloat16> conv_w_all;      // [n_conv][9][C][C]
-    DevBuf<float> bias_all;                // [1 + n_conv][C]
-    CUtensorMap map_conv_w_all;
+    DevBuf<__nv_bfloat16> bias_tiles;      // [1 + n_conv][C][16]: bias as a K-major UMMA operand (hi, lo, 0...)
+    CUtensorMap map_conv_w_all, map_bias_tiles;
     std::vector<CUtensorMap> map_conv_w;
     int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
     int sm_count = SM_COUNT;
@@ -593,8 +593,11 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
                                 __float2bfloat16_rn(f.conv_w[l][((size_t)co * C + ci) * 9 + tap]);
                 for (int c = 0; c < C; ++c) ball[(1 + l) * C + c] = f.conv_b[l][c];
             }
+            std::vector<__nv_bfloat16> btiles;
+            fused_bias_tiles(ball, btiles);
             TC_TRY(upload(m.conv_w_all, wall));
-            TC_TRY(upload(m.bias_all, ball));
+            TC_TRY(upload(m.bias_tiles, btiles));
+            TC_TRY(make_map(&m.map_bias_tiles, m.bias_tiles.p, (uint64_t)(1 + L) * C, 16, (uint32_t)C, 16));
             TC_TRY(make_map(&m.map_conv_w_all, m.conv_w_all.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)C, (uint32_t)C));
         }
     }
@@ -656,8 +659,8 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
     const int total = 2 * m.d.num_residual_blocks;
     if (m.fused && to_flat && n_convs >= total) {
         prof->begin(TC_K_NN_CONV, st);
-        launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.fused_G, m.fused_T, total, I, batch, count_dev, states, obs,
-                           m.bias_all.p, m.flat.p, m.sm_count, st);
+        launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.map_bias_tiles, m.fused_G, m.fused_T, total, I, batch,
+                           count_dev, states, obs, m.flat.p, m.sm_count, st);
         prof->end(st);
         ++launches;
         return -1;

@@ -10,11 +10,15 @@
 // address is moved by 10*dy+dx rows — measured exact on B200 with matrix base offset 0, i.e. the swizzle XOR is
 // a function of the absolute shared-memory address.
 //
-// Roles (320 threads): warp 0 streams the next layer's weights with TMA while the current layer computes;
-// warp 1 issues tcgen05.mma (9 taps x C/16 per tile) and commits one mbarrier per tile; warps 2-9 are two
-// epilogue groups (tcgen05.ld -> bias (+ residual from smem) -> ReLU -> bf16 -> swizzled st.shared) and also
-// build the observation planes from the packed positions at the start of a group.
+// Everything linear is done by the tensor pipe, so the epilogue is only ReLU + bf16 pack + store:
+//   bias      = one K=16 UMMA  (all-ones A tile) x (bias split in bf16 hi+lo on two K slots)
+//   residual  = C/16 UMMAs     (block input X, unshifted) x (identity tile)
+// With N = C a UMMA is only a few cycles of tensor work, so a single issuing thread cannot keep the pipe busy
+// (measured: ~130 cycles per issue).  Eight worker warps therefore each issue the UMMAs of their own tiles
+// (one elected lane, descriptors kept in uniform registers) and then run the epilogue of tile quarters.
+// Warp 0 streams the next layer's weights with TMA while the current layer computes.
 #include <algorithm>
+#include <vector>
 
 #include "nn_bf16.cuh"
 #include "nn_fused.cuh"
@@ -23,7 +27,8 @@
 
 namespace tc {
 
-constexpr int FUSED_THREADS = 320;
+constexpr int WORKERS = 8;
+constexpr int FUSED_THREADS = 32 * (1 + WORKERS);
 constexpr int LEAD = 16;                 // zero rows in front of the first position of a group
 constexpr int MAX_TILES = 16;
 
@@ -36,7 +41,6 @@ struct FusedParams {
     int in_planes;
     const uint32_t *states;  // packed positions, or
     const float *obs;        // dense planes [row][in_planes][81]
-    const float *bias;       // [(1 + n_conv)][C]
     __nv_bfloat16 *out;      // compact [row][81][C] (fc1 input)
 };
 
@@ -48,20 +52,57 @@ __device__ __forceinline__ uint32_t swz(uint32_t off)       // byte offset insid
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits, __nv_bfloat162 zero2)
+{
+    __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(__uint_as_float(a_bits), __uint_as_float(b_bits)), zero2);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// descriptor = constant high word per layout + (shared address >> 4) in the low word
+template <int SW>
+__device__ __forceinline__ uint64_t desc_of(uint32_t saddr)
+{
+    constexpr uint32_t layout = SW == 128 ? 2u : (SW == 64 ? 4u : 6u);
+    constexpr uint32_t hi = ((8u * SW) >> 4) | (1u << 14) | (layout << 29);
+    return ((uint64_t)hi << 32) | (uint64_t)(saddr >> 4);
+}
+
 template <int C>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_constant__ CUtensorMap tmW_stem,
                                                                   const __grid_constant__ CUtensorMap tmW_conv,
+                                                                  const __grid_constant__ CUtensorMap tmBias,
                                                                   FusedParams P)
 {
     constexpr int SW = 2 * C;                                   // activation row = one swizzle span
     constexpr int W_TAP = (C * SW + 1023) & ~1023;              // one conv tap [C x C]
-    constexpr int WS_TAP = (C * 32 + 1023) & ~1023;             // one stem tap [C x 16]
+    constexpr int WS_TAP = (C * 32 + 1023) & ~1023;             // one stem tap / bias tile [C x 16]
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int rows = LEAD + 128 * P.T + 16;
     const int buf_bytes = (rows * SW + 1023) & ~1023;
-    uint8_t *X = smem, *Y = smem + buf_bytes, *W = smem + 2 * buf_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(W + 9 * W_TAP);
+    uint8_t *X = smem, *Y = smem + buf_bytes;
+    uint8_t *W = smem + 2 * buf_bytes;                          // 9 taps of the current layer
+    uint8_t *Bt = W + 9 * W_TAP;                                // bias tile of the current layer
+    uint8_t *Id = Bt + WS_TAP;                                  // identity [C x C]
+    uint8_t *Ones = Id + W_TAP;                                 // 128 rows x 16 ones
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Ones + 4096);
     uint64_t *tdone = bars, *wfull = bars + MAX_TILES, *wfree = bars + MAX_TILES + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + MAX_TILES + 2);
 
@@ -70,39 +111,55 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     if (P.count_dev) count = min(count, *P.count_dev);
     const int n_groups = (count + P.G - 1) / P.G;
     const int n_layers = 1 + P.n_conv;
+    const int issuers = min(WORKERS, P.T);
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < P.T * C) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int t = 0; t < MAX_TILES; ++t) mbar_init(tdone + t, 1);
         mbar_init(wfull, 1);
-        mbar_init(wfree, 1);
+        mbar_init(wfree, (uint32_t)issuers);
         fence_barrier_init();
         tma_prefetch_desc(&tmW_stem);
         tma_prefetch_desc(&tmW_conv);
+        tma_prefetch_desc(&tmBias);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
     // pad rows of both activation buffers must read as zero for ever: clear everything once
     for (int i = threadIdx.x; i < 2 * buf_bytes / 16; i += FUSED_THREADS)
         reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < W_TAP / 16; i += FUSED_THREADS) reinterpret_cast<uint4 *>(Id)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 4096 / 16; i += FUSED_THREADS)
+        reinterpret_cast<uint4 *>(Ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    __syncthreads();
+    if (threadIdx.x < C)            // identity, K-major rows of SW bytes in the swizzle pattern
+        *reinterpret_cast<__nv_bfloat16 *>(Id + swz<SW>((uint32_t)threadIdx.x * SW + (uint32_t)threadIdx.x * 2u)) =
+            __float2bfloat16_rn(1.f);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
 
     uint32_t lcount = 0;       // layers executed so far by this CTA (mbarrier phase = lcount & 1)
     if (warp == 0 && lane == 0 && (int)blockIdx.x < n_groups) {
-        mbar_expect_tx(wfull, 9u * C * 32u);
+        mbar_expect_tx(wfull, 10u * C * 32u);
         for (int tap = 0; tap < 9; ++tap) tma_load_2d(W + tap * WS_TAP, &tmW_stem, wfull, 0, tap * C);
+        tma_load_2d(Bt, &tmBias, wfull, 0, 0);
     }
+
+    const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y), w_addr = smem_u32(W);
+    const uint64_t ones_desc = desc_of<32>(smem_u32(Ones)), bias_desc = desc_of<32>(smem_u32(Bt));
+    const uint32_t id_addr = smem_u32(Id);
+    const uint32_t idesc = make_instr_desc(C);
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 
     for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
         const int pos0 = group * P.G;
         // ---- observation planes of the group -> channels 0..15 of the group's rows in Y (activation layout:
         //      the stem's UMMAs read K = 16 of it; pad rows are never touched and stay zero) ----
-        if (warp >= 2) {
-            for (int idx = threadIdx.x - 64; idx < P.G * 81; idx += FUSED_THREADS - 64) {
+        if (warp >= 1) {
+            for (int idx = threadIdx.x - 32; idx < P.G * 81; idx += FUSED_THREADS - 32) {
                 const int g = idx / 81, a = idx - 81 * g;
                 const int row = pos0 + g;
                 float v[16];
@@ -127,13 +184,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                             if (c < P.in_planes) v[c] = P.obs[((size_t)row * P.in_planes + c) * 81 + a];
                     }
                 }
-                uint4 o[2];
-                __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(o);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) op[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+                o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+                o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
                 const uint32_t off = (uint32_t)(LEAD + 100 * g + (a / 9) * 10 + a % 9) * (uint32_t)SW;
-                *reinterpret_cast<uint4 *>(Y + swz<SW>(off)) = o[0];
-                *reinterpret_cast<uint4 *>(Y + swz<SW>(off + 16)) = o[1];
+                *reinterpret_cast<uint4 *>(Y + swz<SW>(off)) = o0;
+                *reinterpret_cast<uint4 *>(Y + swz<SW>(off + 16)) = o1;
             }
             fence_async_smem();
         }
@@ -142,68 +200,72 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
         for (int l = 0; l < n_layers; ++l, ++lcount) {
             const uint32_t ph = lcount & 1u;
             // layer 0: planes(Y) -> X;  odd l (first conv of a block): X -> Y;  even l > 0: Y -> X, + residual X
-            uint8_t *src = (l == 0 || (l & 1) == 0) ? Y : X;
-            uint8_t *dst = (l & 1) ? Y : X;
+            const bool to_y = (l & 1) != 0;
+            const uint32_t s_addr = to_y ? x_addr : y_addr;
+            uint8_t *dst = to_y ? Y : X;
             const bool last = l == n_layers - 1;
+            const bool residual = l > 0 && !to_y;
             if (warp == 0) {
                 if (lane == 0) {
-                    // once this layer's MMAs have consumed the weights, stream in the next layer's
+                    // once this layer's UMMAs have consumed the weights, stream in the next layer's
                     mbar_wait(wfree, ph);
                     const bool more_layers = l + 1 < n_layers;
                     const bool more_groups = group + (int)gridDim.x < n_groups;
                     if (more_layers) {
-                        mbar_expect_tx(wfull, 9u * C * (uint32_t)SW);
+                        mbar_expect_tx(wfull, 9u * C * (uint32_t)SW + C * 32u);
                         for (int tap = 0; tap < 9; ++tap)
                             tma_load_2d(W + tap * W_TAP, &tmW_conv, wfull, 0, (l * 9 + tap) * C);
+                        tma_load_2d(Bt, &tmBias, wfull, 0, (l + 1) * C);
                     } else if (more_groups) {
-                        mbar_expect_tx(wfull, 9u * C * 32u);
+                        mbar_expect_tx(wfull, 10u * C * 32u);
                         for (int tap = 0; tap < 9; ++tap) tma_load_2d(W + tap * WS_TAP, &tmW_stem, wfull, 0, tap * C);
+                        tma_load_2d(Bt, &tmBias, wfull, 0, 0);
                     }
                 }
-            } else if (warp == 1) {
-                if (lane == 0) {
-                    const uint32_t idesc = make_instr_desc(C);
+            } else {
+                const int e = warp - 1;
+                // ===== issue the UMMAs of this worker's tiles (warp-uniform code, one elected lane issues) =====
+                if (e < issuers) {
                     mbar_wait(wfull, ph);
                     tc_fence_after();
-                    const uint32_t s_addr = smem_u32(src), w_addr = smem_u32(W);
-                    // Consecutive UMMAs into the SAME accumulator serialise on the tensor pipe's latency (N = C is a
-                    // few cycles of work each), so the issue order interleaves the tiles of a chunk: tap-major,
-                    // tile-minor.  Two chunks per layer let the epilogue of the first overlap the MMAs of the second.
-                    const int half = (P.T + 1) / 2;
-                    for (int t0 = 0; t0 < P.T; t0 += half) {
-                        const int t1 = min(P.T, t0 + half);
+                    if (elect_one()) {
+                        for (int t = e; t < P.T; t += WORKERS)          // accumulator starts as the bias
+                            umma_bf16(tmem_base + (uint32_t)(t * C), ones_desc, bias_desc, idesc, 0u);
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
                             const int shift0 = LEAD + (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             if (l == 0) {
-                                const uint64_t bdesc = make_smem_desc<32>(w_addr + (uint32_t)(tap * WS_TAP));
-                                for (int t = t0; t < t1; ++t)
+                                const uint64_t bdesc = desc_of<32>(w_addr + (uint32_t)(tap * WS_TAP));
+                                for (int t = e; t < P.T; t += WORKERS)
                                     umma_bf16(tmem_base + (uint32_t)(t * C),
-                                              make_smem_desc<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW)), bdesc, idesc,
-                                              (uint32_t)(tap != 0));
+                                              desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW)), bdesc, idesc, 1u);
                             } else {
 #pragma unroll
                                 for (int k = 0; k < C / 16; ++k) {
-                                    const uint64_t bdesc = make_smem_desc<SW>(w_addr + (uint32_t)(tap * W_TAP) + 32 * k);
-                                    for (int t = t0; t < t1; ++t)
+                                    const uint64_t bdesc = desc_of<SW>(w_addr + (uint32_t)(tap * W_TAP) + 32 * k);
+                                    for (int t = e; t < P.T; t += WORKERS)
                                         umma_bf16(tmem_base + (uint32_t)(t * C),
-                                                  make_smem_desc<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW) + 32 * k), bdesc,
-                                                  idesc, (uint32_t)((tap | k) != 0));
+                                                  desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW) + 32 * k), bdesc,
+                                                  idesc, 1u);
                                 }
                             }
                         }
-                        for (int t = t0; t < t1; ++t) umma_commit(tdone + t);
-                    }
-                    umma_commit(wfree);
-                }
-            } else {
-                // ===== epilogue: two groups of four warps, tiles alternate between the groups =====
-                const int ew = warp - 2, quarter = warp & 3, egroup = ew >> 2;
-                float breg[C];
-                const float *bias = P.bias + (size_t)l * C;
+                        if (residual) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) breg[c] = __ldg(bias + c);
-                const bool residual = l > 0 && (l & 1) == 0;
+                            for (int k = 0; k < C / 16; ++k) {
+                                const uint64_t bdesc = desc_of<SW>(id_addr + 32 * k);
+                                for (int t = e; t < P.T; t += WORKERS)
+                                    umma_bf16(tmem_base + (uint32_t)(t * C),
+                                              desc_of<SW>(x_addr + (uint32_t)((LEAD + 128 * t) * SW) + 32 * k), bdesc, idesc, 1u);
+                            }
+                        }
+                        for (int t = e; t < P.T; t += WORKERS) umma_commit(tdone + t);
+                        umma_commit(wfree);
+                    }
+                    __syncwarp();
+                }
+                // ===== epilogue: ReLU + bf16 pack + store; warp e owns lane quarter e%4 of tiles t = e/4 (mod 2) =====
+                const int quarter = warp & 3, egroup = e >> 2;
                 for (int t = egroup; t < P.T; t += 2) {
                     const int q = 128 * t + 32 * quarter + lane;          // padded row inside the group
                     const int g = q / 100, rem = q - 100 * g;
@@ -223,29 +285,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                         if (valid) {
 #pragma unroll
                             for (int j = 0; j < CW; j += 8) {
-                                float v[8];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(acc[j + k]) + breg[c0 + j + k];
-                                const uint32_t so = swz<SW>(row_off + (uint32_t)(c0 + j) * 2u);
-                                if (residual) {
-                                    uint4 rv = *reinterpret_cast<const uint4 *>(X + so);
-                                    const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rv);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        float2 f = __bfloat1622float2(rp[k]);
-                                        v[2 * k] += f.x;
-                                        v[2 * k + 1] += f.y;
-                                    }
-                                }
                                 uint4 ov;
-                                __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&ov);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    op[k] = __floats2bfloat162_rn(fmaxf(v[2 * k], 0.f), fmaxf(v[2 * k + 1], 0.f));
+                                ov.x = relu_pack(acc[j], acc[j + 1], zero2);
+                                ov.y = relu_pack(acc[j + 2], acc[j + 3], zero2);
+                                ov.z = relu_pack(acc[j + 4], acc[j + 5], zero2);
+                                ov.w = relu_pack(acc[j + 6], acc[j + 7], zero2);
                                 if (last)
                                     *reinterpret_cast<uint4 *>(P.out + ((size_t)row * 81 + r * 9 + cc) * C + c0 + j) = ov;
                                 else
-                                    *reinterpret_cast<uint4 *>(dst + so) = ov;
+                                    *reinterpret_cast<uint4 *>(dst + swz<SW>(row_off + (uint32_t)(c0 + j) * 2u)) = ov;
                             }
                         }
                     }
@@ -259,7 +307,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,7 +319,8 @@ static size_t fused_smem_bytes(int C, int T)
     const size_t rows = LEAD + 128 * T + 16;
     const size_t buf = (rows * SW + 1023) & ~(size_t)1023;
     const size_t wtap = (C * SW + 1023) & ~(size_t)1023;
-    return 1024 + 2 * buf + 9 * wtap + (MAX_TILES + 2) * 8 + 16;
+    const size_t wstap = (C * 32 + 1023) & ~(size_t)1023;
+    return 1024 + 2 * buf + 9 * wtap + wstap + wtap + 4096 + (MAX_TILES + 2) * 8 + 16;
 }
 
 bool fused_plan(int C, int &G, int &T)
@@ -286,9 +335,22 @@ bool fused_plan(int C, int &G, int &T)
     return G >= 1;
 }
 
-int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_conv, int G, int T, int n_conv,
-                       int in_planes, int batch, const int *count_dev, const uint32_t *states, const float *obs,
-                       const float *bias_all, __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st)
+// bias of every layer as a K-major bf16 tile [C][16]: k=0 holds the bf16 head of the bias, k=1 the remainder
+void fused_bias_tiles(const std::vector<float> &bias_all, std::vector<__nv_bfloat16> &out)
+{
+    const size_t n = bias_all.size();
+    out.assign(n * 16, __float2bfloat16_rn(0.f));
+    for (size_t i = 0; i < n; ++i) {
+        __nv_bfloat16 hi = __float2bfloat16_rn(bias_all[i]);
+        __nv_bfloat16 lo = __float2bfloat16_rn(bias_all[i] - __bfloat162float(hi));
+        out[i * 16] = hi;
+        out[i * 16 + 1] = lo;
+    }
+}
+
+int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_conv, const CUtensorMap &bias_tiles, int G,
+                       int T, int n_conv, int in_planes, int batch, const int *count_dev, const uint32_t *states,
+                       const float *obs, __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st)
 {
     FusedParams P{};
     P.count_dev = count_dev;
@@ -299,20 +361,19 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
     P.in_planes = in_planes;
     P.states = states;
     P.obs = obs;
-    P.bias = bias_all;
     P.out = out_flat;
     const size_t smem = fused_smem_bytes(C, T);
     const int groups = (batch + G - 1) / G;
     const int grid = std::max(1, std::min(groups, sm_count));
     if (C == 16) {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trunk_fused<16><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, P);
+        k_trunk_fused<16><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
     } else if (C == 32) {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trunk_fused<32><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, P);
+        k_trunk_fused<32><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
     } else {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trunk_fused<64><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, P);
+        k_trunk_fused<64><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
     }
     return TC_OK;
 }

@@ -3,14 +3,17 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace tc {
 
 // largest tile count T (and positions per group G) that fits shared memory and TMEM for C channels
 bool fused_plan(int C, int &G, int &T);
-int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_conv, int G, int T, int n_conv,
-                       int in_planes, int batch, const int *count_dev, const uint32_t *states, const float *obs,
-                       const float *bias_all, __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st);
+void fused_bias_tiles(const std::vector<float> &bias_all, std::vector<__nv_bfloat16> &out);
+int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_conv, const CUtensorMap &bias_tiles, int G,
+                       int T, int n_conv, int in_planes, int batch, const int *count_dev, const uint32_t *states,
+                       const float *obs, __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st);
 
 }  // namespace tc
