@@ -18,6 +18,8 @@
 // (one elected lane, descriptors kept in uniform registers) and then run the epilogue of tile quarters.
 // Warp 0 streams the next layer's weights with TMA while the current layer computes.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "nn_bf16.cuh"
@@ -42,6 +44,7 @@ struct FusedParams {
     const uint32_t *states;  // packed positions, or
     const float *obs;        // dense planes [row][in_planes][81]
     __nv_bfloat16 *out;      // compact [row][81][C] (fc1 input)
+    long long *timeline;     // optional: clock64 stamps of CTA 0 (debugging / profiling aid), else null
 };
 
 template <int SW>
@@ -199,6 +202,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
 
         for (int l = 0; l < n_layers; ++l, ++lcount) {
             const uint32_t ph = lcount & 1u;
+            const bool stamp = P.timeline && blockIdx.x == 0 && group == (int)blockIdx.x && lane == 0;
+            if (stamp && warp == 1) P.timeline[8 * l + 0] = clock64();
             // layer 0: planes(Y) -> X;  odd l (first conv of a block): X -> Y;  even l > 0: Y -> X, + residual X
             const bool to_y = (l & 1) != 0;
             const uint32_t s_addr = to_y ? x_addr : y_addr;
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                 if (e < issuers) {
                     mbar_wait(wfull, ph);
                     tc_fence_after();
+                    if (stamp && warp == 1) P.timeline[8 * l + 1] = clock64();
                     if (elect_one()) {
                         for (int t = e; t < P.T; t += WORKERS)          // accumulator starts as the bias
                             umma_bf16(tmem_base + (uint32_t)(t * C), ones_desc, bias_desc, idesc, 0u);
@@ -263,6 +269,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                         umma_commit(wfree);
                     }
                     __syncwarp();
+                    if (stamp && warp == 1) P.timeline[8 * l + 2] = clock64();
                 }
                 // ===== epilogue: ReLU + bf16 pack + store; warp e owns lane quarter e%4 of tiles t = e/4 (mod 2) =====
                 const int quarter = warp & 3, egroup = e >> 2;
@@ -274,6 +281,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                     const bool valid = g < P.G && row < count && rem < 90 && cc != 9;
                     mbar_wait(tdone + t, ph);
                     tc_fence_after();
+                    if (stamp && warp == 1 && t == egroup) P.timeline[8 * l + 3] = clock64();
                     const uint32_t t_addr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(t * C);
                     const uint32_t row_off = (uint32_t)(LEAD + q) * (uint32_t)SW;
 #pragma unroll
@@ -298,11 +306,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                         }
                     }
                 }
+                if (stamp && warp == 1) P.timeline[8 * l + 4] = clock64();
                 fence_async_smem();       // activations written through the generic proxy feed the next layer's UMMAs
+                if (stamp && warp == 1) P.timeline[8 * l + 5] = clock64();
             }
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
+            if (stamp && warp == 1) P.timeline[8 * l + 6] = clock64();
         }
     }
     tc_fence_before();
@@ -362,6 +373,11 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
     P.states = states;
     P.obs = obs;
     P.out = out_flat;
+    static long long *timeline_dev = nullptr;
+    if (getenv("TACULT_FUSED_TIMELINE")) {
+        if (!timeline_dev) cudaMalloc(&timeline_dev, 8 * 64 * sizeof(long long));
+        P.timeline = timeline_dev;
+    }
     const size_t smem = fused_smem_bytes(C, T);
     const int groups = (batch + G - 1) / G;
     const int grid = std::max(1, std::min(groups, sm_count));
@@ -374,6 +390,17 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
     } else {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_trunk_fused<64><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
+    }
+    if (P.timeline) {
+        long long h[8 * 64];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, timeline_dev, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[fused timeline] layer: start->weights  issue  first-tile-done  epilogue  fence  barrier (cycles)\n");
+        for (int l = 0; l <= n_conv; ++l)
+            fprintf(stderr, "[fused timeline] %2d: %6lld %6lld %6lld %6lld %6lld %6lld | total %6lld\n", l,
+                    h[8 * l + 1] - h[8 * l], h[8 * l + 2] - h[8 * l + 1], h[8 * l + 3] - h[8 * l + 2],
+                    h[8 * l + 4] - h[8 * l + 3], h[8 * l + 5] - h[8 * l + 4], h[8 * l + 6] - h[8 * l + 5],
+                    h[8 * l + 6] - h[8 * l]);
     }
     return TC_OK;
 }
