@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "nn.cuh"
@@ -91,9 +92,15 @@ struct tc_engine {
     int evaluator = TC_EVAL_HASH;
     HashEvalParams hash_params{};
     FoldedNet folded;
-    NetF32 net32;
-    NetBF16 net16;
+    NetF32 net32, net32b;          // one evaluator instance per half (scratch buffers are per instance)
+    NetBF16 net16, net16b;
     bool have_weights = false;
+    // The trees are searched as two independent halves on two streams, so that one half's tree kernels overlap
+    // the other half's network kernels (different SM resources: no shared memory vs. all of it).
+    int n_halves = 1;
+    TreeStore hts[2]{};
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch for tc_forward
     DevBuf<float> fwd_obs, fwd_pi, fwd_v, fwd_logits;
     DevBuf<uint32_t> fwd_states;
@@ -178,7 +185,7 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     TC_ALLOC(e->eval_state, 8 * E);
     TC_ALLOC(e->eval_pi, 81 * E);
     TC_ALLOC(e->eval_v, E);
-    TC_ALLOC(e->eval_count, 1);
+    TC_ALLOC(e->eval_count, 2);
     TC_ALLOC(e->error_flag, 1);
     TC_ALLOC(e->root_states, 8 * E);
     TC_ALLOC(e->root_active, E);
@@ -215,9 +222,38 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     ts.eval_v = e->eval_v.p;
     ts.eval_count = e->eval_count.p;
     ts.error_flag = e->error_flag.p;
+    {
+        const char *hv = getenv("TACULT_HALVES");
+        e->n_halves = (E >= 512 && cfg->eval_log_capacity == 0) ? 2 : 1;
+        if (hv) e->n_halves = atoi(hv) == 2 && E >= 2 ? 2 : 1;
+        const int h0 = e->n_halves == 2 ? (int)((E + 1) / 2) : (int)E;
+        for (int h = 0; h < e->n_halves; ++h) {
+            const size_t t0 = h == 0 ? 0 : (size_t)h0;
+            TreeStore v = ts;
+            v.E = h == 0 ? h0 : (int)E - h0;
+            v.node_hdr = ts.node_hdr + 2 * capN * t0;
+            v.edge_mem = ts.edge_mem + 4 * capE * t0;
+            v.hash = ts.hash + hs * t0;
+            v.ctl = ts.ctl + t0;
+            v.path = ts.path + (size_t)MAX_DEPTH * t0;
+            v.eval_state = ts.eval_state + 8 * t0;
+            v.eval_pi = ts.eval_pi + 81 * t0;
+            v.eval_v = ts.eval_v + t0;
+            v.eval_count = ts.eval_count + h;
+            e->hts[h] = v;
+        }
+        if (e->n_halves == 2) {
+            if (cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+                set_error("tc_create: side stream / events could not be created");
+                return fail(TC_ECUDA);
+            }
+        }
+    }
     cudaMemsetAsync(e->ctl.p, 0, e->ctl.bytes(), e->stream);
     cudaMemsetAsync(e->error_flag.p, 0, sizeof(int), e->stream);
-    cudaMemsetAsync(e->eval_count.p, 0, sizeof(int), e->stream);
+    cudaMemsetAsync(e->eval_count.p, 0, 2 * sizeof(int), e->stream);
     cudaMemsetAsync(e->log_count.p, 0, sizeof(int), e->stream);
     cudaMemsetAsync(e->root_active.p, 0, e->root_active.bytes(), e->stream);
     launch_reset(ts, -1, e->stream);
@@ -236,6 +272,9 @@ extern "C" int tc_destroy(tc_engine *e)
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->side_stream) { cudaStreamSynchronize(e->side_stream); cudaStreamDestroy(e->side_stream); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
     return TC_OK;
 }
@@ -312,38 +351,58 @@ extern "C" int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, co
     return set_roots_dev(e, active_host);
 }
 
-// one lock-step simulation for every tree: select -> evaluate leaves -> expand + backup
-static int enqueue_simulation(tc_engine *e, double cpuct)
+// one lock-step simulation for every tree of half `h`: select -> evaluate leaves -> expand + backup
+static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st)
 {
-    TC_CUDA(cudaMemsetAsync(e->eval_count.p, 0, sizeof(int), e->stream));
-    e->prof.begin(TC_K_SELECT, e->stream);
-    launch_select(e->ts, cpuct, e->stream);
-    e->prof.end(e->stream);
+    const TreeStore &ts = e->hts[h];
+    NetF32 &n32 = h == 0 ? e->net32 : e->net32b;
+    NetBF16 &n16 = h == 0 ? e->net16 : e->net16b;
+    TC_CUDA(cudaMemsetAsync(ts.eval_count, 0, sizeof(int), st));
+    e->prof.begin(TC_K_SELECT, st);
+    launch_select(ts, cpuct, st);
+    e->prof.end(st);
     e->launches += 1;
     if (e->evaluator == TC_EVAL_HASH) {
-        e->prof.begin(TC_K_EVAL_HASH, e->stream);
-        launch_hash_eval(e->ts, e->hash_params, e->stream);
-        e->prof.end(e->stream);
+        e->prof.begin(TC_K_EVAL_HASH, st);
+        launch_hash_eval(ts, e->hash_params, st);
+        e->prof.end(st);
         e->launches += 1;
     } else if (e->evaluator == TC_EVAL_NET_F32) {
-        e->launches += e->net32.forward(e->ts.E, e->eval_count.p, e->eval_state.p, nullptr, e->eval_pi.p, e->eval_v.p,
-                                        nullptr, e->stream, &e->prof);
+        e->launches += n32.forward(ts.E, ts.eval_count, ts.eval_state, nullptr, ts.eval_pi, ts.eval_v, nullptr, st, &e->prof);
     } else {
-        int n = e->net16.forward(e->ts.E, e->eval_count.p, e->eval_state.p, nullptr, e->eval_pi.p, e->eval_v.p,
-                                 nullptr, e->stream, &e->prof);
+        int n = n16.forward(ts.E, ts.eval_count, ts.eval_state, nullptr, ts.eval_pi, ts.eval_v, nullptr, st, &e->prof);
         if (n < 0) return n;
         e->launches += n;
     }
-    if (e->cfg.eval_log_capacity > 0) {
-        k_log_append<<<64, 256, 0, e->stream>>>(e->ts, e->log_states.p, e->log_pi.p, e->log_v.p, e->log_count.p,
-                                                e->cfg.eval_log_capacity);
-        k_log_advance<<<1, 1, 0, e->stream>>>(e->ts, e->log_count.p);
+    if (e->cfg.eval_log_capacity > 0) {      // single-half mode only (tc_create)
+        k_log_append<<<64, 256, 0, st>>>(ts, e->log_states.p, e->log_pi.p, e->log_v.p, e->log_count.p,
+                                         e->cfg.eval_log_capacity);
+        k_log_advance<<<1, 1, 0, st>>>(ts, e->log_count.p);
         e->launches += 2;
     }
-    e->prof.begin(TC_K_EXPAND_BACKUP, e->stream);
-    launch_expand_backup(e->ts, e->stream);
-    e->prof.end(e->stream);
+    e->prof.begin(TC_K_EXPAND_BACKUP, st);
+    launch_expand_backup(ts, st);
+    e->prof.end(st);
     e->launches += 1;
+    return TC_OK;
+}
+
+// `num_sims` lock-step simulations of every tree; with two halves the second runs on the side stream
+static int enqueue_search(tc_engine *e, int num_sims, double cpuct)
+{
+    if (num_sims <= 0) return TC_OK;
+    if (e->n_halves == 2) {
+        TC_CUDA(cudaEventRecord(e->ev_fork, e->stream));
+        TC_CUDA(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+    }
+    for (int s = 0; s < num_sims; ++s) {
+        TC_TRY(enqueue_simulation(e, cpuct, 0, e->stream));
+        if (e->n_halves == 2) TC_TRY(enqueue_simulation(e, cpuct, 1, e->side_stream));
+    }
+    if (e->n_halves == 2) {
+        TC_CUDA(cudaEventRecord(e->ev_join, e->side_stream));
+        TC_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+    }
     return TC_OK;
 }
 
@@ -385,7 +444,7 @@ extern "C" int tc_search(tc_engine *e, int num_sims, double cpuct)
     TC_TRY(check_engine(e));
     TC_CHECK(num_sims >= 0, TC_EINVAL, "tc_search: negative num_sims");
     TC_TRY(check_evaluator_ready(e));
-    for (int s = 0; s < num_sims; ++s) TC_TRY(enqueue_simulation(e, cpuct));
+    TC_TRY(enqueue_search(e, num_sims, cpuct));
     TC_CUDA(cudaGetLastError());
     return check_device_errors(e);
 }
@@ -469,9 +528,14 @@ extern "C" int tc_load_weights(tc_engine *e, const tc_net_desc *desc, const floa
     TC_TRY(fold_blob(*desc, blob_host, n_floats, e->folded));
     TC_CHECK(desc->channels < 32 || desc->channels % 32 == 0, TC_EINVAL,
              "channels must be < 32 or a multiple of 32, got %d", desc->channels);
-    const int cap = std::max(e->ts.E, 1);
+    if (e->side_stream) TC_CUDA(cudaStreamSynchronize(e->side_stream));
+    const int cap = std::max(e->hts[0].E, 1);
     TC_TRY(e->net32.upload(e->folded, cap));
     e->net16.upload(e->folded, cap);       // optional: records why_not when the shape is unsupported
+    if (e->n_halves == 2) {
+        TC_TRY(e->net32b.upload(e->folded, std::max(e->hts[1].E, 1)));
+        e->net16b.upload(e->folded, std::max(e->hts[1].E, 1));
+    }
     e->have_weights = true;
     return TC_OK;
 }
@@ -570,7 +634,7 @@ extern "C" int tc_debug_trunk(tc_engine *e, int evaluator, int batch, const uint
     TC_TRY(check_engine(e));
     TC_CHECK(e->have_weights, TC_ESTATE, "tc_debug_trunk: tc_load_weights has not been called");
     TC_CHECK(batch >= 1 && batch <= e->net32.capacity && states_host && out_host && n_convs >= 0, TC_EINVAL,
-             "tc_debug_trunk: bad argument (batch must be <= num_envs)");
+             "tc_debug_trunk: bad argument (batch must be <= %d)", e->net32.capacity);
     const size_t n = (size_t)batch * 81 * e->folded.d.channels;
     DevBuf<uint32_t> st;
     DevBuf<float> out;
@@ -637,7 +701,7 @@ extern "C" int tc_selfplay_step(tc_engine *e, int plies)
         launch_set_roots(e->ts, e->root_states.p, e->root_active.p, e->stream);
         e->prof.end(e->stream);
         e->launches += 2;
-        for (int s = 0; s < e->sp_cfg.num_sims; ++s) TC_TRY(enqueue_simulation(e, e->sp_cfg.cpuct));
+        TC_TRY(enqueue_search(e, e->sp_cfg.num_sims, e->sp_cfg.cpuct));
         e->prof.begin(TC_K_OTHER, e->stream);
         launch_selfplay_move(e->ts, e->sp, e->sp_cfg, e->stream);
         e->launches += 1;

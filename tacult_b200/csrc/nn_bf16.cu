@@ -577,11 +577,8 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
         int G = 0, T = 0;
         m.fused = m.stem_on_tensor && (!fz || atoi(fz) != 0) && fused_plan(C, G, T);
         if (m.fused) {
-            // balance the persistent grid: as few groups per CTA as the capacity needs, all of about the same size
-            const int waves = (cap + m.sm_count * G - 1) / (m.sm_count * G);
-            const int g_bal = (cap + m.sm_count * waves - 1) / (m.sm_count * waves);
-            m.fused_G = std::max(1, std::min(G, g_bal));
-            m.fused_T = (100 * m.fused_G + 127) / 128;
+            m.fused_G = G;          // maxima; the kernel balances its groups from the live leaf count
+            m.fused_T = T;
             std::vector<__nv_bfloat16> wall(std::max<size_t>(1, L) * 9 * C * C);
             std::vector<float> ball((1 + L) * (size_t)C);
             for (int c = 0; c < C; ++c) ball[c] = f.stem_b[c];

@@ -112,9 +112,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int count = P.batch;
     if (P.count_dev) count = min(count, *P.count_dev);
-    const int n_groups = (count + P.G - 1) / P.G;
+    // group size chosen from the LIVE count so that the persistent grid is evenly loaded (P.G / P.T are the maxima
+    // the shared-memory carve-up was sized for)
+    const int waves = max(1, (count + (int)gridDim.x * P.G - 1) / ((int)gridDim.x * P.G));
+    const int G = max(1, min(P.G, (count + (int)gridDim.x * waves - 1) / ((int)gridDim.x * waves)));
+    const int T = (100 * G + 127) / 128;
+    const int n_groups = (count + G - 1) / G;
     const int n_layers = 1 + P.n_conv;
-    const int issuers = min(WORKERS, P.T);
+    const int issuers = min(WORKERS, T);
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < P.T * C) tmem_cols <<= 1;
 
@@ -158,11 +163,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 
     for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
-        const int pos0 = group * P.G;
+        const int pos0 = group * G;
         // ---- observation planes of the group -> channels 0..15 of the group's rows in Y (activation layout:
         //      the stem's UMMAs read K = 16 of it; pad rows are never touched and stay zero) ----
         if (warp >= 1) {
-            for (int idx = threadIdx.x - 32; idx < P.G * 81; idx += FUSED_THREADS - 32) {
+            for (int idx = threadIdx.x - 32; idx < G * 81; idx += FUSED_THREADS - 32) {
                 const int g = idx / 81, a = idx - 81 * g;
                 const int row = pos0 + g;
                 float v[16];
@@ -235,21 +240,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                     tc_fence_after();
                     if (stamp && warp == 1) P.timeline[8 * l + 1] = clock64();
                     if (elect_one()) {
-                        for (int t = e; t < P.T; t += WORKERS)          // accumulator starts as the bias
+                        for (int t = e; t < T; t += WORKERS)          // accumulator starts as the bias
                             umma_bf16(tmem_base + (uint32_t)(t * C), ones_desc, bias_desc, idesc, 0u);
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
                             const int shift0 = LEAD + (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             if (l == 0) {
                                 const uint64_t bdesc = desc_of<32>(w_addr + (uint32_t)(tap * WS_TAP));
-                                for (int t = e; t < P.T; t += WORKERS)
+                                for (int t = e; t < T; t += WORKERS)
                                     umma_bf16(tmem_base + (uint32_t)(t * C),
                                               desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW)), bdesc, idesc, 1u);
                             } else {
 #pragma unroll
                                 for (int k = 0; k < C / 16; ++k) {
                                     const uint64_t bdesc = desc_of<SW>(w_addr + (uint32_t)(tap * W_TAP) + 32 * k);
-                                    for (int t = e; t < P.T; t += WORKERS)
+                                    for (int t = e; t < T; t += WORKERS)
                                         umma_bf16(tmem_base + (uint32_t)(t * C),
                                                   desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW) + 32 * k), bdesc,
                                                   idesc, 1u);
@@ -260,12 +265,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
 #pragma unroll
                             for (int k = 0; k < C / 16; ++k) {
                                 const uint64_t bdesc = desc_of<SW>(id_addr + 32 * k);
-                                for (int t = e; t < P.T; t += WORKERS)
+                                for (int t = e; t < T; t += WORKERS)
                                     umma_bf16(tmem_base + (uint32_t)(t * C),
                                               desc_of<SW>(x_addr + (uint32_t)((LEAD + 128 * t) * SW) + 32 * k), bdesc, idesc, 1u);
                             }
                         }
-                        for (int t = e; t < P.T; t += WORKERS) umma_commit(tdone + t);
+                        for (int t = e; t < T; t += WORKERS) umma_commit(tdone + t);
                         umma_commit(wfree);
                     }
                     __syncwarp();
@@ -273,12 +278,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                 }
                 // ===== epilogue: ReLU + bf16 pack + store; warp e owns lane quarter e%4 of tiles t = e/4 (mod 2) =====
                 const int quarter = warp & 3, egroup = e >> 2;
-                for (int t = egroup; t < P.T; t += 2) {
+                for (int t = egroup; t < T; t += 2) {
                     const int q = 128 * t + 32 * quarter + lane;          // padded row inside the group
                     const int g = q / 100, rem = q - 100 * g;
                     const int r = rem / 10, cc = rem - 10 * r;
                     const int row = pos0 + g;
-                    const bool valid = g < P.G && row < count && rem < 90 && cc != 9;
+                    const bool valid = g < G && row < count && rem < 90 && cc != 9;
                     mbar_wait(tdone + t, ph);
                     tc_fence_after();
                     if (stamp && warp == 1 && t == egroup) P.timeline[8 * l + 3] = clock64();
@@ -379,8 +384,7 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
         P.timeline = timeline_dev;
     }
     const size_t smem = fused_smem_bytes(C, T);
-    const int groups = (batch + G - 1) / G;
-    const int grid = std::max(1, std::min(groups, sm_count));
+    const int grid = std::max(1, std::min(batch, sm_count));     // the kernel sizes its groups from the live count
     if (C == 16) {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_trunk_fused<16><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
