@@ -35,7 +35,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int SH_ROWS = 160;        // shifted variant: rows [g0-16, g0+144) of the activation per 128-row tile
 constexpr int SH_LEAD = 16;
 
-enum { OUT_PADDED_BF16 = 0, OUT_COMPACT_BF16 = 1, OUT_F32 = 2 };
+enum { OUT_PADDED_BF16 = 0, OUT_COMPACT_BF16 = 1, OUT_F32 = 2, OUT_PLAIN_BF16 = 3, OUT_HEADS = 4 };
 
 struct GemmParams {
     const int *count_dev;     // live positions (may be null)
@@ -55,6 +55,8 @@ struct GemmParams {
     const float *bias;
     const __nv_bfloat16 *residual;   // padded layout, may be null
     void *out;
+    float *out_v;             // OUT_HEADS: value head [row]
+    float *out_logits;        // OUT_HEADS: optional raw policy logits [row][81]
 };
 
 __device__ __forceinline__ int live_count(const int *count_dev, int batch)
@@ -67,7 +69,7 @@ __device__ __forceinline__ int live_count(const int *count_dev, int batch)
 // ------------------------------------------------------------------------------------------------
 // the GEMM / implicit-conv kernel
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_K>
+template <int BLOCK_K, bool HEADS>
 __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, GemmParams P)
 {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
             const int q = 128 * mt + 32 * quarter + lane;      // GEMM row of this thread
             bool valid;
             size_t out_row;
-            if (P.mode == OUT_F32) {
+            if (P.mode == OUT_F32 || P.mode == OUT_PLAIN_BF16 || P.mode == OUT_HEADS) {
                 valid = q < m_total;
                 out_row = (size_t)q;
             } else {
@@ -222,6 +224,43 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
             mbar_wait(tfull + as, aphase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(as * P.block_n);
+            if constexpr (HEADS) {
+                // policy + value heads: N = 96 columns (81 logits, the value pre-activation, padding).  The whole row
+                // sits in this thread's registers, so the unmasked softmax (network.py:99) needs no shuffles.
+                uint32_t a0[32], a1[32], a2[32];
+                tmem_ld32(t_base, a0);
+                tmem_ld32(t_base + 32u, a1);
+                tmem_ld32(t_base + 64u, a2);
+                tmem_ld_wait();
+                if (valid) {
+                    float lg[96];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        lg[j] = __uint_as_float(a0[j]) + __ldg(P.bias + j);
+                        lg[32 + j] = __uint_as_float(a1[j]) + __ldg(P.bias + 32 + j);
+                        lg[64 + j] = __uint_as_float(a2[j]) + __ldg(P.bias + 64 + j);
+                    }
+                    float mx = lg[0];
+#pragma unroll
+                    for (int j = 1; j < 81; ++j) mx = fmaxf(mx, lg[j]);
+                    if (P.out_logits) {
+                        float *lo = P.out_logits + out_row * 81;
+#pragma unroll
+                        for (int j = 0; j < 81; ++j) lo[j] = lg[j];
+                    }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 81; ++j) {
+                        lg[j] = __expf(lg[j] - mx);
+                        sum += lg[j];
+                    }
+                    const float inv = 1.f / sum;
+                    float *po = reinterpret_cast<float *>(P.out) + out_row * 81;
+#pragma unroll
+                    for (int j = 0; j < 81; ++j) po[j] = lg[j] * inv;
+                    P.out_v[out_row] = tanhf(lg[81]);
+                }
+            } else {
             const int cw = P.block_n < 32 ? 16 : 32;
             for (int c0 = 0; c0 < P.block_n; c0 += cw) {
                 uint32_t acc[32];
@@ -244,7 +283,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
                         }
                     } else {
                         __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(P.out) + out_row * P.ldc + n0 + c0;
-                        const __nv_bfloat16 *res = P.residual ? P.residual + (size_t)(PAD0 + q) * P.ldc + n0 + c0 : nullptr;
+                        const __nv_bfloat16 *res = (P.residual && P.mode != OUT_PLAIN_BF16)
+                                                       ? P.residual + (size_t)(PAD0 + q) * P.ldc + n0 + c0 : nullptr;
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             if (j >= cw) break;
@@ -273,6 +313,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
                         }
                     }
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();
@@ -442,7 +483,12 @@ struct NetBF16Impl {
     size_t act_rows = 0;
     DevBuf<__nv_bfloat16> act[3];          // padded layout
     DevBuf<__nv_bfloat16> flat;            // compact [cap][81*C], fc1 input
-    DevBuf<float> emb;                     // [cap][E]
+    DevBuf<float> emb;                     // [cap][E]   (fallback heads path)
+    DevBuf<__nv_bfloat16> emb16;           // [cap][E]   fc1 output feeding the tensor-core heads
+    DevBuf<__nv_bfloat16> head_w16;        // [96][E]: 81 policy rows, the value row, zero padding
+    DevBuf<float> head_b96;
+    CUtensorMap map_emb16, map_head_w;
+    bool heads_on_tensor = false;
     DevBuf<float> stem_w, stem_b;
     DevBuf<__nv_bfloat16> planes;          // padded layout, 16 channels (observation planes, zero padded)
     DevBuf<__nv_bfloat16> stem_w16;        // [9][C][16]
@@ -568,6 +614,24 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     TC_CUDA(m.flat.alloc(flat_rows * 81 * C));
     TC_CUDA(cudaMemset(m.flat.p, 0, m.flat.bytes()));
     TC_CUDA(m.emb.alloc((size_t)cap * E));
+    m.heads_on_tensor = E % 64 == 0;
+    if (m.heads_on_tensor) {
+        const size_t emb_rows = std::max(cap, 128);
+        TC_CUDA(m.emb16.alloc(emb_rows * E));
+        TC_CUDA(cudaMemset(m.emb16.p, 0, m.emb16.bytes()));
+        std::vector<__nv_bfloat16> hw16((size_t)96 * E, __float2bfloat16_rn(0.f));
+        std::vector<float> hb96(96, 0.f);
+        for (int o = 0; o < 81; ++o) {
+            for (int k = 0; k < E; ++k) hw16[(size_t)o * E + k] = __float2bfloat16_rn(f.pi_w[(size_t)o * E + k]);
+            hb96[o] = f.pi_b[o];
+        }
+        for (int k = 0; k < E; ++k) hw16[(size_t)81 * E + k] = __float2bfloat16_rn(f.v_w[k]);
+        hb96[81] = f.v_b[0];
+        TC_TRY(upload(m.head_w16, hw16));
+        TC_TRY(upload(m.head_b96, hb96));
+        TC_TRY(make_map(&m.map_emb16, m.emb16.p, (uint64_t)emb_rows, (uint64_t)E, 128, 64));
+        TC_TRY(make_map(&m.map_head_w, m.head_w16.p, 96, (uint64_t)E, 96, 64));
+    }
     m.fc1_block_n = E % 64 == 0 ? 64 : (E % 32 == 0 ? 32 : 16);
     TC_TRY(make_map(&m.map_flat, m.flat.p, (uint64_t)flat_rows, (uint64_t)81 * C, 128, 64));
     TC_TRY(make_map(&m.map_fc1, m.fc1_w.p, (uint64_t)E, (uint64_t)81 * C, (uint32_t)m.fc1_block_n, 64));
@@ -601,9 +665,10 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     const size_t budget = 200 * 1024;
     m.conv_stages = pick_stages(m.block_k, C, C <= 64 ? 48 * 1024 : budget);
     m.fc1_stages = pick_stages(64, m.fc1_block_n, 96 * 1024);
-    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     return TC_OK;
 }
 
@@ -639,9 +704,10 @@ static void launch_gemm(const NetBF16Impl &m, int block_k, const CUtensorMap &a,
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(max_tiles, m.sm_count * per_sm);
     if (grid < 1) grid = 1;
-    if (block_k == 64) k_gemm_tc<64><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
-    else if (block_k == 32) k_gemm_tc<32><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
-    else k_gemm_tc<16><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+    if (P.mode == OUT_HEADS) k_gemm_tc<64, true><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+    else if (block_k == 64) k_gemm_tc<64, false><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+    else if (block_k == 32) k_gemm_tc<32, false><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+    else k_gemm_tc<16, false><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
 }
 
 void launch_heads_f32(int batch, const int *count_dev, int E, const float *emb, const float *W, const float *bias,
@@ -755,17 +821,38 @@ int NetBF16::forward(int batch, const int *count_dev, const uint32_t *states, co
     P.a_row0 = 0;
     P.b_tap_rows = 0;
     P.stages = m.fc1_stages;
-    P.mode = OUT_F32;
+    P.mode = m.heads_on_tensor ? OUT_PLAIN_BF16 : OUT_F32;
     P.relu = 1;
     P.ldc = E;
     P.bias = m.fc1_b.p;
     P.residual = nullptr;
-    P.out = m.emb.p;
+    P.out = m.heads_on_tensor ? (void *)m.emb16.p : (void *)m.emb.p;
     prof->begin(TC_K_NN_FC1, st);
     launch_gemm(m, 64, m.map_flat, m.map_fc1, P, ((batch + 127) / 128) * P.n_blocks, st);
     prof->end(st);
     prof->begin(TC_K_NN_HEADS, st);
-    launch_heads_f32(batch, count_dev, E, m.emb.p, m.head_w.p, m.head_b.p, pi, v, logits, st);
+    if (m.heads_on_tensor) {
+        GemmParams H{};
+        H.count_dev = count_dev;
+        H.batch = batch;
+        H.rows_per_unit = 1;
+        H.taps = 1;
+        H.k_chunks = E / 64;
+        H.block_n = 96;
+        H.n_blocks = 1;
+        H.a_row0 = 0;
+        H.b_tap_rows = 0;
+        H.stages = pick_stages(64, 96, 96 * 1024);
+        H.mode = OUT_HEADS;
+        H.ldc = 81;
+        H.bias = m.head_b96.p;
+        H.out = pi;
+        H.out_v = v;
+        H.out_logits = logits;
+        launch_gemm(m, 64, m.map_emb16, m.map_head_w, H, (batch + 127) / 128, st);
+    } else {
+        launch_heads_f32(batch, count_dev, E, m.emb.p, m.head_w.p, m.head_b.p, pi, v, logits, st);
+    }
     prof->end(st);
     launches += 2;
     return launches;
