@@ -191,12 +191,66 @@ def gen_rules(name):
     print(name, "games", len(res))
 
 
+def gen_callers(ref, name):
+    """Reference VectorizedArena.playGames and Coach.generateTrainExamples under fixed np.random seeds; the
+    oracle restatements (oracle/callers_oracle.py) must reproduce them draw for draw."""
+    import contextlib
+    import hashlib
+    import io
+    from callers_oracle import arena_play_games, selfplay_iteration
+    dotdict = ref.utils.dotdict
+    arena_rows = []
+    for seed in (0, 1, 2):
+        args = dotdict(numEnvs=6, numMCTSSims=3, cpuct=2.4)
+        np.random.seed(seed)
+        g = ref.utac_game.UtacGame()
+        m1, m2 = (ref.mcts.VectorizedMCTS(g, HashEvaluator(k), args) for k in (1, 2))
+        ar = ref.arena.VectorizedArena(lambda x: np.argmax(m1.getActionProbs(x, temps=np.zeros(6)), axis=1),
+                                       lambda x: np.argmax(m2.getActionProbs(x, temps=np.zeros(6)), axis=1), g, None, 6)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = ar.playGames(20)
+        np.random.seed(seed)
+        og = OracleGame()
+        o1, o2 = (OracleVectorizedMCTS(og, HashEvaluator(k), args) for k in (1, 2))
+        got = arena_play_games(og, lambda x: np.argmax(o1.getActionProbs(x, temps=np.zeros(6)), axis=1),
+                               lambda x: np.argmax(o2.getActionProbs(x, temps=np.zeros(6)), axis=1), 20, 6)
+        assert tuple(want) == tuple(got), (want, got)
+        arena_rows.append([seed, *want])
+
+    class FakeNet:
+        def __init__(self):
+            self.h = HashEvaluator(5)
+
+        def predict(self, obs):
+            return self.h.predict(obs)
+    args = dotdict(numEnvs=4, minNumEps=4, numMCTSSims=6, cpuct=2.4, tempThreshold=5)
+    coach = ref.coach.Coach.__new__(ref.coach.Coach)
+    coach.game, coach.args, coach.pnet = ref.utac_game.UtacGame(), args, FakeNet()
+    np.random.seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_ex = coach.generateTrainExamples()
+    np.random.seed(7)
+    og = OracleGame()
+    or_ex = selfplay_iteration(og, OracleVectorizedMCTS(og, HashEvaluator(5), args), args)
+    assert len(ref_ex) == len(or_ex)
+    h = hashlib.sha256()
+    for a, b in zip(ref_ex, or_ex):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2]
+        h.update(a[0].numpy().tobytes())
+        h.update(a[1].numpy().tobytes())
+        h.update(np.float64(a[2]).tobytes())
+    np.savez_compressed(os.path.join(HERE, name), arena=np.array(arena_rows), coach_examples=len(ref_ex),
+                        coach_sha256=np.frombuffer(h.digest(), dtype=np.uint8))
+    print(name, "arena", arena_rows, "coach examples", len(ref_ex))
+
+
 def main():
     import logging
     logging.disable(logging.ERROR)   # the zero-prior fallback logs an error per hit (mcts.py:281)
     ref = ref_loader.load_reference()
     torch.manual_seed(0)
     gen_rules("rules_playouts.npz")
+    gen_callers(ref, "callers.npz")
     gen_symmetries(ref, "symmetries.npz")
     gen_net(ref, "net_tiny.npz", seed=1, channels=8, blocks=1, emb=32, n_pos=48)
     gen_net(ref, "net_trainer_default.npz", seed=2, channels=32, blocks=3, emb=256, n_pos=70)
