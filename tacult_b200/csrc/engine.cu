@@ -92,15 +92,15 @@ struct tc_engine {
     int evaluator = TC_EVAL_HASH;
     HashEvalParams hash_params{};
     FoldedNet folded;
-    NetF32 net32, net32b;          // one evaluator instance per half (scratch buffers are per instance)
-    NetBF16 net16, net16b;
+    NetF32 net32, net32x[3];       // one evaluator instance per part (scratch buffers are per instance)
+    NetBF16 net16, net16x[3];
     bool have_weights = false;
     // The trees are searched as two independent halves on two streams, so that one half's tree kernels overlap
     // the other half's network kernels (different SM resources: no shared memory vs. all of it).
-    int n_halves = 1;
-    TreeStore hts[2]{};
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int n_halves = 1;              // number of parts (1, 2 or 4), each on its own stream
+    TreeStore hts[4]{};
+    cudaStream_t side_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     // scratch for tc_forward
     DevBuf<float> fwd_obs, fwd_pi, fwd_v, fwd_logits;
     DevBuf<uint32_t> fwd_states;
@@ -185,7 +185,7 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     TC_ALLOC(e->eval_state, 8 * E);
     TC_ALLOC(e->eval_pi, 81 * E);
     TC_ALLOC(e->eval_v, E);
-    TC_ALLOC(e->eval_count, 2);
+    TC_ALLOC(e->eval_count, 4);
     TC_ALLOC(e->error_flag, 1);
     TC_ALLOC(e->root_states, 8 * E);
     TC_ALLOC(e->root_active, E);
@@ -225,12 +225,15 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     {
         const char *hv = getenv("TACULT_HALVES");
         e->n_halves = (E >= 512 && cfg->eval_log_capacity == 0) ? 2 : 1;
-        if (hv) e->n_halves = atoi(hv) == 2 && E >= 2 ? 2 : 1;
-        const int h0 = e->n_halves == 2 ? (int)((E + 1) / 2) : (int)E;
+        if (hv) {
+            const int want = atoi(hv);
+            e->n_halves = (want == 4 && E >= 4) ? 4 : ((want == 2 && E >= 2) ? 2 : 1);
+        }
+        const int per = (int)((E + e->n_halves - 1) / e->n_halves);
         for (int h = 0; h < e->n_halves; ++h) {
-            const size_t t0 = h == 0 ? 0 : (size_t)h0;
+            const size_t t0 = (size_t)h * per;
             TreeStore v = ts;
-            v.E = h == 0 ? h0 : (int)E - h0;
+            v.E = std::min(per, (int)E - (int)t0);
             v.node_hdr = ts.node_hdr + 2 * capN * t0;
             v.edge_mem = ts.edge_mem + 4 * capE * t0;
             v.hash = ts.hash + hs * t0;
@@ -242,18 +245,20 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
             v.eval_count = ts.eval_count + h;
             e->hts[h] = v;
         }
-        if (e->n_halves == 2) {
-            if (cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-                set_error("tc_create: side stream / events could not be created");
+        if (e->n_halves > 1) {
+            bool ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+            for (int h = 1; h < e->n_halves && ok; ++h)
+                ok = cudaStreamCreateWithFlags(&e->side_stream[h - 1], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&e->ev_join[h - 1], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) {
+                set_error("tc_create: side streams / events could not be created");
                 return fail(TC_ECUDA);
             }
         }
     }
     cudaMemsetAsync(e->ctl.p, 0, e->ctl.bytes(), e->stream);
     cudaMemsetAsync(e->error_flag.p, 0, sizeof(int), e->stream);
-    cudaMemsetAsync(e->eval_count.p, 0, 2 * sizeof(int), e->stream);
+    cudaMemsetAsync(e->eval_count.p, 0, 4 * sizeof(int), e->stream);
     cudaMemsetAsync(e->log_count.p, 0, sizeof(int), e->stream);
     cudaMemsetAsync(e->root_active.p, 0, e->root_active.bytes(), e->stream);
     launch_reset(ts, -1, e->stream);
@@ -272,9 +277,11 @@ extern "C" int tc_destroy(tc_engine *e)
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
-    if (e->side_stream) { cudaStreamSynchronize(e->side_stream); cudaStreamDestroy(e->side_stream); }
+    for (int h = 0; h < 3; ++h) {
+        if (e->side_stream[h]) { cudaStreamSynchronize(e->side_stream[h]); cudaStreamDestroy(e->side_stream[h]); }
+        if (e->ev_join[h]) cudaEventDestroy(e->ev_join[h]);
+    }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-    if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
     return TC_OK;
 }
@@ -355,8 +362,8 @@ extern "C" int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, co
 static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st)
 {
     const TreeStore &ts = e->hts[h];
-    NetF32 &n32 = h == 0 ? e->net32 : e->net32b;
-    NetBF16 &n16 = h == 0 ? e->net16 : e->net16b;
+    NetF32 &n32 = h == 0 ? e->net32 : e->net32x[h - 1];
+    NetBF16 &n16 = h == 0 ? e->net16 : e->net16x[h - 1];
     TC_CUDA(cudaMemsetAsync(ts.eval_count, 0, sizeof(int), st));
     e->prof.begin(TC_K_SELECT, st);
     launch_select(ts, cpuct, st);
@@ -391,17 +398,16 @@ static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st
 static int enqueue_search(tc_engine *e, int num_sims, double cpuct)
 {
     if (num_sims <= 0) return TC_OK;
-    if (e->n_halves == 2) {
+    if (e->n_halves > 1) {
         TC_CUDA(cudaEventRecord(e->ev_fork, e->stream));
-        TC_CUDA(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+        for (int h = 1; h < e->n_halves; ++h) TC_CUDA(cudaStreamWaitEvent(e->side_stream[h - 1], e->ev_fork, 0));
     }
-    for (int s = 0; s < num_sims; ++s) {
-        TC_TRY(enqueue_simulation(e, cpuct, 0, e->stream));
-        if (e->n_halves == 2) TC_TRY(enqueue_simulation(e, cpuct, 1, e->side_stream));
-    }
-    if (e->n_halves == 2) {
-        TC_CUDA(cudaEventRecord(e->ev_join, e->side_stream));
-        TC_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+    for (int s = 0; s < num_sims; ++s)
+        for (int h = 0; h < e->n_halves; ++h)
+            TC_TRY(enqueue_simulation(e, cpuct, h, h == 0 ? e->stream : e->side_stream[h - 1]));
+    for (int h = 1; h < e->n_halves; ++h) {
+        TC_CUDA(cudaEventRecord(e->ev_join[h - 1], e->side_stream[h - 1]));
+        TC_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join[h - 1], 0));
     }
     return TC_OK;
 }
@@ -528,13 +534,14 @@ extern "C" int tc_load_weights(tc_engine *e, const tc_net_desc *desc, const floa
     TC_TRY(fold_blob(*desc, blob_host, n_floats, e->folded));
     TC_CHECK(desc->channels < 32 || desc->channels % 32 == 0, TC_EINVAL,
              "channels must be < 32 or a multiple of 32, got %d", desc->channels);
-    if (e->side_stream) TC_CUDA(cudaStreamSynchronize(e->side_stream));
+    for (int h = 0; h < 3; ++h)
+        if (e->side_stream[h]) TC_CUDA(cudaStreamSynchronize(e->side_stream[h]));
     const int cap = std::max(e->hts[0].E, 1);
     TC_TRY(e->net32.upload(e->folded, cap));
     e->net16.upload(e->folded, cap);       // optional: records why_not when the shape is unsupported
-    if (e->n_halves == 2) {
-        TC_TRY(e->net32b.upload(e->folded, std::max(e->hts[1].E, 1)));
-        e->net16b.upload(e->folded, std::max(e->hts[1].E, 1));
+    for (int h = 1; h < e->n_halves; ++h) {
+        TC_TRY(e->net32x[h - 1].upload(e->folded, std::max(e->hts[h].E, 1)));
+        e->net16x[h - 1].upload(e->folded, std::max(e->hts[h].E, 1));
     }
     e->have_weights = true;
     return TC_OK;

@@ -33,6 +33,11 @@ def pack_gamestates(boards):
             continue
         gs = gs_owner._get_gs()
         if int(gs.side) != 1:
+            # the arena keeps passing finished boards whose side to move is not the current player
+            # (arena.py:176-184); the reference's search only looks up their terminal value and does nothing
+            if gs_owner.is_terminal():
+                active[i] = 0
+                continue
             raise ValueError("VectorizedMCTS expects canonical boards (side == 1), as getCanonicalForm returns")
         b[i] = np.asarray(gs.board, dtype=np.uint32)
         o[i] = np.asarray(gs.occ, dtype=np.uint32)
