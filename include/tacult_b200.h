@@ -93,6 +93,8 @@ typedef struct {
 } tc_stats;
 
 int         tc_abi_version(void);
+/* free / total bytes of HBM on `device` (used by the host side to size tree pools) */
+int         tc_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 const char *tc_last_error(void);
 
 /* ---- rules engine hooks: replace utac_gym.core.GameState methods (external C++ `utac`;

@@ -99,6 +99,7 @@ _pi = ctypes.POINTER(ctypes.c_int)
 SYMBOLS = {
     "tc_abi_version": (_i, []),
     "tc_last_error": (ctypes.c_char_p, []),
+    "tc_device_memory": (_i, [_i, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "tc_rules_step": (_i, [_i, _vp, _vp, _vp, _vp]),
     "tc_rules_legal_mask": (_i, [_i, _vp, _vp]),
     "tc_rules_status": (_i, [_i, _vp, _vp]),

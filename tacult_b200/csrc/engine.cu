@@ -142,6 +142,17 @@ static int check_device_errors(tc_engine *e)
 extern "C" int tc_abi_version(void) { return TC_ABI_VERSION; }
 extern "C" const char *tc_last_error(void) { return g_error; }
 
+extern "C" int tc_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes)
+{
+    TC_CHECK(free_bytes && total_bytes, TC_EINVAL, "tc_device_memory: null output");
+    TC_CUDA(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    TC_CUDA(cudaMemGetInfo(&f, &t));
+    *free_bytes = f;
+    *total_bytes = t;
+    return TC_OK;
+}
+
 extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
 {
     TC_CHECK(cfg && out, TC_EINVAL, "tc_create: null argument");

@@ -6,6 +6,8 @@ Same constructor and methods (`getActionProbs`, `search`, `reset`), same return 
 expansion, backup, move generation and the network forward all run on the GPU through the C ABI;
 this class only converts between `GameState` objects and packed positions.
 """
+import ctypes
+
 import numpy as np
 
 from . import _lib
@@ -26,10 +28,19 @@ class VectorizedMCTS:
         self.args = args
         num_envs = int(args.numEnvs)
         sims = int(args.numMCTSSims)
-        # the reference never prunes: a tree can grow by one node per simulation for every ply of the game
-        cap_nodes = int(_opt(args, "tc_max_nodes_per_tree", 0)) or (sims * 82 + 64)
-        cap_edges = int(_opt(args, "tc_max_edges_per_tree", 0)) or (12 * cap_nodes + 1024)
         device = int(_opt(args, "tc_device", 0))
+        # The reference never prunes and never resets: a tree grows by up to one node per simulation for every
+        # ply of every game played on that env index (an arena replays several games on the same trees,
+        # arena.py:216-305).  Default: room for 4 games, clamped to 40% of the free HBM, never below one game.
+        one_game = sims * 82 + 64
+        cap_nodes = int(_opt(args, "tc_max_nodes_per_tree", 0))
+        if not cap_nodes:
+            free, total = ctypes.c_uint64(), ctypes.c_uint64()
+            _lib.check(_lib.load().tc_device_memory(device, ctypes.byref(free), ctypes.byref(total)))
+            per_node = 32 + 8 + 12 * 32          # header + hash slots + edges
+            budget = int(0.4 * free.value / max(1, num_envs) / per_node)
+            cap_nodes = max(one_game, min(4 * one_game, budget))
+        cap_edges = int(_opt(args, "tc_max_edges_per_tree", 0)) or (12 * cap_nodes + 1024)
         self.engine = Engine(num_envs, cap_nodes, cap_edges, device=device,
                              eval_log_capacity=int(_opt(args, "tc_eval_log_capacity", 0)))
         self._bind_evaluator(nnet, args)
