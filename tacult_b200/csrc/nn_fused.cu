@@ -29,8 +29,9 @@
 
 namespace tc {
 
-constexpr int WORKERS = 8;
-constexpr int FUSED_THREADS = 32 * (1 + WORKERS);
+constexpr int ISSUERS = 4;               // warps 1..4: one elected lane each issues the UMMAs of tiles t = i (mod 4)
+constexpr int EPI_WARPS = 8;             // warps 5..12: two per TMEM lane quarter
+constexpr int FUSED_THREADS = 32 * (1 + ISSUERS + EPI_WARPS);
 constexpr int LEAD = 16;                 // zero rows in front of the first position of a group
 constexpr int MAX_TILES = 16;
 
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     const int T = (100 * G + 127) / 128;
     const int n_groups = (count + G - 1) / G;
     const int n_layers = 1 + P.n_conv;
-    const int issuers = min(WORKERS, T);
+    const int issuers = min(ISSUERS, T);
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < P.T * C) tmem_cols <<= 1;
 
@@ -166,8 +167,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
         const int pos0 = group * G;
         // ---- observation planes of the group -> channels 0..15 of the group's rows in Y (activation layout:
         //      the stem's UMMAs read K = 16 of it; pad rows are never touched and stay zero) ----
-        if (warp >= 1) {
-            for (int idx = threadIdx.x - 32; idx < G * 81; idx += FUSED_THREADS - 32) {
+        if (warp > ISSUERS) {
+            for (int idx = threadIdx.x - 32 * (1 + ISSUERS); idx < G * 81; idx += 32 * EPI_WARPS) {
                 const int g = idx / 81, a = idx - 81 * g;
                 const int row = pos0 + g;
                 float v[16];
@@ -232,29 +233,29 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                         tma_load_2d(Bt, &tmBias, wfull, 0, 0);
                     }
                 }
-            } else {
+            } else if (warp <= ISSUERS) {
                 const int e = warp - 1;
-                // ===== issue the UMMAs of this worker's tiles (warp-uniform code, one elected lane issues) =====
+                // ===== issue the UMMAs of this warp's tiles (warp-uniform code, one elected lane issues) =====
                 if (e < issuers) {
                     mbar_wait(wfull, ph);
                     tc_fence_after();
                     if (stamp && warp == 1) P.timeline[8 * l + 1] = clock64();
                     if (elect_one()) {
-                        for (int t = e; t < T; t += WORKERS)          // accumulator starts as the bias
+                        for (int t = e; t < T; t += ISSUERS)          // accumulator starts as the bias
                             umma_bf16(tmem_base + (uint32_t)(t * C), ones_desc, bias_desc, idesc, 0u);
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
                             const int shift0 = LEAD + (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             if (l == 0) {
                                 const uint64_t bdesc = desc_of<32>(w_addr + (uint32_t)(tap * WS_TAP));
-                                for (int t = e; t < T; t += WORKERS)
+                                for (int t = e; t < T; t += ISSUERS)
                                     umma_bf16(tmem_base + (uint32_t)(t * C),
                                               desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW)), bdesc, idesc, 1u);
                             } else {
 #pragma unroll
                                 for (int k = 0; k < C / 16; ++k) {
                                     const uint64_t bdesc = desc_of<SW>(w_addr + (uint32_t)(tap * W_TAP) + 32 * k);
-                                    for (int t = e; t < T; t += WORKERS)
+                                    for (int t = e; t < T; t += ISSUERS)
                                         umma_bf16(tmem_base + (uint32_t)(t * C),
                                                   desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW) + 32 * k), bdesc,
                                                   idesc, 1u);
@@ -265,19 +266,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
 #pragma unroll
                             for (int k = 0; k < C / 16; ++k) {
                                 const uint64_t bdesc = desc_of<SW>(id_addr + 32 * k);
-                                for (int t = e; t < T; t += WORKERS)
+                                for (int t = e; t < T; t += ISSUERS)
                                     umma_bf16(tmem_base + (uint32_t)(t * C),
                                               desc_of<SW>(x_addr + (uint32_t)((LEAD + 128 * t) * SW) + 32 * k), bdesc, idesc, 1u);
                             }
                         }
-                        for (int t = e; t < T; t += WORKERS) umma_commit(tdone + t);
+                        for (int t = e; t < T; t += ISSUERS) umma_commit(tdone + t);
                         umma_commit(wfree);
                     }
                     __syncwarp();
                     if (stamp && warp == 1) P.timeline[8 * l + 2] = clock64();
                 }
-                // ===== epilogue: ReLU + bf16 pack + store; warp e owns lane quarter e%4 of tiles t = e/4 (mod 2) =====
-                const int quarter = warp & 3, egroup = e >> 2;
+            } else {
+                // ===== epilogue: ReLU + bf16 pack + store; two warps per TMEM lane quarter, tiles alternate =====
+                const int quarter = warp & 3, egroup = (warp - 1 - ISSUERS) >> 2;
                 for (int t = egroup; t < T; t += 2) {
                     const int q = 128 * t + 32 * quarter + lane;          // padded row inside the group
                     const int g = q / 100, rem = q - 100 * g;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                     const bool valid = g < G && row < count && rem < 90 && cc != 9;
                     mbar_wait(tdone + t, ph);
                     tc_fence_after();
-                    if (stamp && warp == 1 && t == egroup) P.timeline[8 * l + 3] = clock64();
+                    if (stamp && warp == 1 + ISSUERS && t == egroup) P.timeline[8 * l + 3] = clock64();
                     const uint32_t t_addr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(t * C);
                     const uint32_t row_off = (uint32_t)(LEAD + q) * (uint32_t)SW;
 #pragma unroll
@@ -311,9 +313,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                         }
                     }
                 }
-                if (stamp && warp == 1) P.timeline[8 * l + 4] = clock64();
+                if (stamp && warp == 1 + ISSUERS) P.timeline[8 * l + 4] = clock64();
                 fence_async_smem();       // activations written through the generic proxy feed the next layer's UMMAs
-                if (stamp && warp == 1) P.timeline[8 * l + 5] = clock64();
+                if (stamp && warp == 1 + ISSUERS) P.timeline[8 * l + 5] = clock64();
             }
             tc_fence_before();
             __syncthreads();
