@@ -632,7 +632,11 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
         TC_TRY(make_map(&m.map_emb16, m.emb16.p, (uint64_t)emb_rows, (uint64_t)E, 128, 64));
         TC_TRY(make_map(&m.map_head_w, m.head_w16.p, 96, (uint64_t)E, 96, 64));
     }
-    m.fc1_block_n = E % 64 == 0 ? 64 : (E % 32 == 0 ? 32 : 16);
+    {
+        const char *fb = getenv("TACULT_FC1_BLOCK_N");
+        m.fc1_block_n = E % 64 == 0 ? 64 : (E % 32 == 0 ? 32 : 16);
+        if (fb && atoi(fb) > 0 && E % atoi(fb) == 0 && atoi(fb) % 32 == 0 && atoi(fb) <= 256) m.fc1_block_n = atoi(fb);
+    }
     TC_TRY(make_map(&m.map_flat, m.flat.p, (uint64_t)flat_rows, (uint64_t)81 * C, 128, 64));
     TC_TRY(make_map(&m.map_fc1, m.fc1_w.p, (uint64_t)E, (uint64_t)81 * C, (uint32_t)m.fc1_block_n, 64));
 
@@ -664,7 +668,7 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     }
     const size_t budget = 200 * 1024;
     m.conv_stages = pick_stages(m.block_k, C, C <= 64 ? 48 * 1024 : budget);
-    m.fc1_stages = pick_stages(64, m.fc1_block_n, 96 * 1024);
+    m.fc1_stages = pick_stages(64, m.fc1_block_n, m.fc1_block_n > 64 ? 200 * 1024 : 96 * 1024);
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));

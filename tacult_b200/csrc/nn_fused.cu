@@ -241,37 +241,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                     tc_fence_after();
                     if (stamp && warp == 1) P.timeline[8 * l + 1] = clock64();
                     if (elect_one()) {
-                        for (int t = e; t < T; t += ISSUERS)          // accumulator starts as the bias
-                            umma_bf16(tmem_base + (uint32_t)(t * C), ones_desc, bias_desc, idesc, 0u);
+                        // tile by tile, so that a finished tile's epilogue overlaps the UMMAs of the next ones; the four
+                        // issuers keep four independent accumulators in flight on the tensor pipe
+                        for (int t = e; t < T; t += ISSUERS) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(t * C);
+                            const uint32_t a_tile = s_addr + (uint32_t)((LEAD + 128 * t) * SW);
+                            umma_bf16(d_tmem, ones_desc, bias_desc, idesc, 0u);      // accumulator starts as the bias
 #pragma unroll 1
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int shift0 = LEAD + (tap / 3 - 1) * 10 + (tap % 3 - 1);
-                            if (l == 0) {
-                                const uint64_t bdesc = desc_of<32>(w_addr + (uint32_t)(tap * WS_TAP));
-                                for (int t = e; t < T; t += ISSUERS)
-                                    umma_bf16(tmem_base + (uint32_t)(t * C),
-                                              desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW)), bdesc, idesc, 1u);
-                            } else {
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int shift = ((tap / 3 - 1) * 10 + (tap % 3 - 1)) * SW;
+                                if (l == 0) {
+                                    umma_bf16(d_tmem, desc_of<SW>(a_tile + (uint32_t)shift),
+                                              desc_of<32>(w_addr + (uint32_t)(tap * WS_TAP)), idesc, 1u);
+                                } else {
 #pragma unroll
-                                for (int k = 0; k < C / 16; ++k) {
-                                    const uint64_t bdesc = desc_of<SW>(w_addr + (uint32_t)(tap * W_TAP) + 32 * k);
-                                    for (int t = e; t < T; t += ISSUERS)
-                                        umma_bf16(tmem_base + (uint32_t)(t * C),
-                                                  desc_of<SW>(s_addr + (uint32_t)((shift0 + 128 * t) * SW) + 32 * k), bdesc,
-                                                  idesc, 1u);
+                                    for (int k = 0; k < C / 16; ++k)
+                                        umma_bf16(d_tmem, desc_of<SW>(a_tile + (uint32_t)shift + 32 * k),
+                                                  desc_of<SW>(w_addr + (uint32_t)(tap * W_TAP) + 32 * k), idesc, 1u);
                                 }
                             }
-                        }
-                        if (residual) {
+                            if (residual) {
 #pragma unroll
-                            for (int k = 0; k < C / 16; ++k) {
-                                const uint64_t bdesc = desc_of<SW>(id_addr + 32 * k);
-                                for (int t = e; t < T; t += ISSUERS)
-                                    umma_bf16(tmem_base + (uint32_t)(t * C),
-                                              desc_of<SW>(x_addr + (uint32_t)((LEAD + 128 * t) * SW) + 32 * k), bdesc, idesc, 1u);
+                                for (int k = 0; k < C / 16; ++k)
+                                    umma_bf16(d_tmem, desc_of<SW>(x_addr + (uint32_t)((LEAD + 128 * t) * SW) + 32 * k),
+                                              desc_of<SW>(id_addr + 32 * k), idesc, 1u);
                             }
+                            umma_commit(tdone + t);
                         }
-                        for (int t = e; t < T; t += ISSUERS) umma_commit(tdone + t);
                         umma_commit(wfree);
                     }
                     __syncwarp();
