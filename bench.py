@@ -334,8 +334,9 @@ def roofline(prof, k0, k1, a, evaluator, flops_eval):
     # backup RMW per level, expansion writes header + edges, reads pi/v, writes the 32-byte leaf position
     sel_bytes = 16.0 * d["sum_legal"] + 40.0 * d["sum_depth"] + 32.0 * d["sum_depth"]
     exp_bytes = 32.0 * d["sum_depth"] + (64.0 + 328.0 + 32.0) * d["nn_leaves"] + 24.0 * d["sum_leaf_legal"]
-    conv_layers = 2 * NET["num_residual_blocks"]
-    conv_flops = 2.0 * 81 * 9 * NET["channels"] * NET["channels"] * d["nn_leaves"] * conv_layers
+    # trunk = conv_in + the residual-block convolutions (one fused launch for this net): SURVEY.md §8d trunk term
+    trunk_flops_per_leaf = 2.0 * 81 * 9 * NET["channels"] * (4 + 2 * NET["num_residual_blocks"] * NET["channels"])
+    conv_flops = trunk_flops_per_leaf * d["nn_leaves"]
     if "select" in kernels:
         kernels["select"].update(bound="hbm", achieved=sel_bytes / (kernels["select"]["ms"] * 1e-3) / 1e9, unit="GB/s")
     if "expand_backup" in kernels:
@@ -361,8 +362,9 @@ def roofline(prof, k0, k1, a, evaluator, flops_eval):
     roof = {"kernel": top, "bound": tk.get("bound", "tensor"), "achieved": tk.get("achieved"), "peak": peak,
             "unit": tk.get("unit", "TFLOP/s"), "frac": (tk.get("achieved") or 0.0) / peak, "traffic": traffic,
             "peak_source": peaks["source"], "avg_launch_us": tk["avg_us"], "share_of_step": tk["share"],
-            "rows_per_launch": d["nn_leaves"] / max(kernels.get("nn_conv", {}).get("launches", 0) / conv_layers, 1)
-            if top.startswith("nn_") else None}
+            "rows_per_launch": d["nn_leaves"] / max(kernels.get("nn_conv", {}).get("launches", 0), 1)
+            if top.startswith("nn_") else None,
+            "algorithmic_flops_per_leaf": trunk_flops_per_leaf if top == "nn_conv" else None}
     return roof, kernels
 
 
