@@ -332,8 +332,12 @@ def roofline(prof, k0, k1, a, evaluator, flops_eval):
     sims_steps = max(d["sims"], 1)
     # algorithmic bytes of the tree side per simulation: select reads P,Q,N per legal edge + header,
     # backup RMW per level, expansion writes header + edges, reads pi/v, writes the 32-byte leaf position
-    sel_bytes = 16.0 * d["sum_legal"] + 40.0 * d["sum_depth"] + 32.0 * d["sum_depth"]
-    exp_bytes = 32.0 * d["sum_depth"] + (64.0 + 328.0 + 32.0) * d["nn_leaves"] + 24.0 * d["sum_leaf_legal"]
+    # (layout in DESIGN.md §3): select reads the 32-byte edge records of every level, writes the path, and at a new
+    # leaf reads the parent header, probes 128 B of the hash table, writes header + 16 B per edge + the 32-byte leaf
+    sel_bytes = 32.0 * d["sum_legal"] + 8.0 * d["sum_depth"] + (32.0 + 128.0 + 32.0 + 32.0) * d["nn_leaves"] \
+        + 16.0 * d["sum_leaf_legal"]
+    # expand/backup: header + pi/v of the leaf, 8 B prior per edge, 24 B read-modify-write per path level
+    exp_bytes = (32.0 + 328.0) * d["nn_leaves"] + 8.0 * d["sum_leaf_legal"] + 32.0 * d["sum_depth"]
     # trunk = conv_in + the residual-block convolutions (one fused launch for this net): SURVEY.md §8d trunk term
     trunk_flops_per_leaf = 2.0 * 81 * 9 * NET["channels"] * (4 + 2 * NET["num_residual_blocks"] * NET["channels"])
     conv_flops = trunk_flops_per_leaf * d["nn_leaves"]
