@@ -6,12 +6,26 @@ namespace tc {
 // ---------------------------------------------------------------------------------------------
 // small warp helpers
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fmix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    return h ^ (h >> 16);
+}
+
+// 32-bit arithmetic only (the table needs a slot index and an independent 12-bit tag, nothing cryptographic):
+// low word -> slot, bits 40..51 -> tag
 __device__ __forceinline__ uint64_t key_hash(const Pos &p)
 {
-    uint64_t k0 = (uint64_t)p.mine[0] | ((uint64_t)p.mine[1] << 32);
-    uint64_t k1 = (uint64_t)p.mine[2] | ((uint64_t)p.occ[0] << 32);
-    uint64_t k2 = (uint64_t)p.occ[1] | ((uint64_t)p.occ[2] << 32);
-    return mix64(k0 ^ mix64(k1 ^ mix64(k2 ^ mix64((uint64_t)p.last))));
+    const uint32_t K = 0x9E3779B1u;
+    uint32_t x = p.mine[0];
+    x = x * K + p.mine[1];
+    x = x * K + p.mine[2];
+    x = x * K + p.occ[0];
+    x = x * K + p.occ[1];
+    x = x * K + p.occ[2];
+    x = x * K + p.last;
+    return ((uint64_t)fmix32(x ^ 0x68E31DA4u) << 32) | (uint64_t)fmix32(x);
 }
 
 __device__ __forceinline__ void unpack_hdr(const uint4 &h0, const uint4 &h1, Pos &p, uint32_t &n_edges,
@@ -276,36 +290,56 @@ __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
             EdgeBlock eb = edge_block(ts, tree, off, n);
             EdgeRegs e[3];
             uint32_t nsum = 0;
+            e[0].N = e[1].N = e[2].N = 0;
+            if ((uint32_t)lane < n) {
+                e[0].P = eb.P[lane];
+                e[0].Q = eb.Q[lane];
+                e[0].N = eb.N[lane];
+                e[0].child = eb.child[lane];
+                e[0].coff = eb.coff[lane];
+                e[0].meta = eb.meta[lane];
+                nsum = e[0].N;
+            }
+            if (n > 32) {                                   // wide nodes only (free moves: up to 81 edges)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const uint32_t j = (uint32_t)lane + 32u * q;
-                e[q].N = 0;
-                if (j < n) {
-                    e[q].P = eb.P[j];
-                    e[q].Q = eb.Q[j];
-                    e[q].N = eb.N[j];
-                    e[q].child = eb.child[j];
-                    e[q].coff = eb.coff[j];
-                    e[q].meta = eb.meta[j];
-                    nsum += e[q].N;
+                for (int q = 1; q < 3; ++q) {
+                    const uint32_t j = (uint32_t)lane + 32u * q;
+                    if (j < n) {
+                        e[q].P = eb.P[j];
+                        e[q].Q = eb.Q[j];
+                        e[q].N = eb.N[j];
+                        e[q].child = eb.child[j];
+                        e[q].coff = eb.coff[j];
+                        e[q].meta = eb.meta[j];
+                        nsum += e[q].N;
+                    }
                 }
             }
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) nsum += __shfl_xor_sync(FULL, nsum, d);     // Ns[s]
 
             // PUCT over the legal edges (mcts.py:301-316)
-            const double sq_visited = __dsqrt_rn((double)nsum);
+            const double sq_visited = nsum ? __dsqrt_rn((double)nsum) : 0.0;      // only used by edges with N > 0
             const double sq_fresh = __dsqrt_rn(__dadd_rn((double)nsum, 1e-8));
             double best_u = -INFINITY;
             int best_j = 1 << 20;
+            if ((uint32_t)lane < n) {
+                double cpp = __dmul_rn(cpuct, e[0].P);
+                best_u = e[0].N ? __dadd_rn(e[0].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[0].N)))
+                                : __dmul_rn(cpp, sq_fresh);
+                best_j = lane;
+                if (!(best_u > -INFINITY)) { best_u = -INFINITY; best_j = 1 << 20; }   // NaN / -inf is never selected (mcts.py:314)
+            }
+            if (n > 32) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const uint32_t j = (uint32_t)lane + 32u * q;
-                if (j < n) {
-                    double cpp = __dmul_rn(cpuct, e[q].P);
-                    double u = e[q].N ? __dadd_rn(e[q].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[q].N)))
-                                      : __dmul_rn(cpp, sq_fresh);
-                    if (u > best_u) { best_u = u; best_j = (int)j; }       // ascending j: first maximum wins
+                for (int q = 1; q < 3; ++q) {
+                    const uint32_t j = (uint32_t)lane + 32u * q;
+                    if (j < n) {
+                        double cpp = __dmul_rn(cpuct, e[q].P);
+                        double u = e[q].N ? __dadd_rn(e[q].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[q].N)))
+                                          : __dmul_rn(cpp, sq_fresh);
+                        if (u > best_u) { best_u = u; best_j = (int)j; }   // ascending j: first maximum wins
+                    }
                 }
             }
 #pragma unroll
