@@ -315,8 +315,7 @@ __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
                     }
                 }
             }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) nsum += __shfl_xor_sync(FULL, nsum, d);     // Ns[s]
+            nsum = __reduce_add_sync(FULL, nsum);                                          // Ns[s]
 
             // PUCT over the legal edges (mcts.py:301-316)
             const double sq_visited = nsum ? __dsqrt_rn((double)nsum) : 0.0;      // only used by edges with N > 0
@@ -342,16 +341,22 @@ __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
                     }
                 }
             }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                double ou = __shfl_xor_sync(FULL, best_u, d);
-                int oj = __shfl_xor_sync(FULL, best_j, d);
-                // edges are in action order, so "lowest action index wins ties" (strict '>' in mcts.py:314) is
-                // "lowest j wins"; a lane that found nothing carries j = 2^20 and never wins
-                if (oj < (1 << 20) && (best_j >= (1 << 20) || ou > best_u || (ou == best_u && oj < best_j))) {
-                    best_u = ou;
-                    best_j = oj;
+            // Warp arg-max in three REDUX steps instead of a 5-round shuffle butterfly: doubles are mapped to
+            // order-preserving unsigned keys (-0.0 folded into +0.0 first, so equal values give equal keys exactly
+            // as the reference's strict '>' sees them); max of the high words, max of the low words among the
+            // lanes that hold that high word, then the lowest edge index among the lanes that hold the maximum
+            // (edges are in action order: "lowest action index wins ties", mcts.py:314).
+            {
+                unsigned long long key = 0ull;                 // lanes without a candidate can never win
+                if (best_j < (1 << 20)) {
+                    long long bits = __double_as_longlong(__dadd_rn(best_u, 0.0));
+                    key = (unsigned long long)bits ^ (bits < 0 ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
                 }
+                const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+                const uint32_t mhi = __reduce_max_sync(FULL, hi);
+                const uint32_t mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+                const bool top = best_j < (1 << 20) && hi == mhi && lo == mlo;
+                best_j = (int)__reduce_min_sync(FULL, top ? (uint32_t)best_j : (uint32_t)(1 << 20));
             }
             sum_legal += n;
             if (best_j >= (1 << 20)) {       // cannot happen for a live position; park the tree loudly
