@@ -369,15 +369,18 @@ extern "C" int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, co
     return set_roots_dev(e, active_host);
 }
 
-// one lock-step simulation for every tree of half `h`: select -> evaluate leaves -> expand + backup
-static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st)
+// One lock-step simulation for every tree of part `h`: select -> evaluate leaves -> expand + backup.
+// Inside a run of simulations the backup of simulation k and the descent of simulation k+1 share a launch
+// (`first` = no pending backup, `last` = no following descent).
+static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st, bool first, bool last)
 {
     const TreeStore &ts = e->hts[h];
     NetF32 &n32 = h == 0 ? e->net32 : e->net32x[h - 1];
     NetBF16 &n16 = h == 0 ? e->net16 : e->net16x[h - 1];
     TC_CUDA(cudaMemsetAsync(ts.eval_count, 0, sizeof(int), st));
     e->prof.begin(TC_K_SELECT, st);
-    launch_select(ts, cpuct, st);
+    if (first) launch_select(ts, cpuct, st);
+    else launch_backup_select(ts, cpuct, st);
     e->prof.end(st);
     e->launches += 1;
     if (e->evaluator == TC_EVAL_HASH) {
@@ -398,10 +401,12 @@ static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st
         k_log_advance<<<1, 1, 0, st>>>(ts, e->log_count.p);
         e->launches += 2;
     }
-    e->prof.begin(TC_K_EXPAND_BACKUP, st);
-    launch_expand_backup(ts, st);
-    e->prof.end(st);
-    e->launches += 1;
+    if (last) {
+        e->prof.begin(TC_K_EXPAND_BACKUP, st);
+        launch_expand_backup(ts, st);
+        e->prof.end(st);
+        e->launches += 1;
+    }
     return TC_OK;
 }
 
@@ -415,7 +420,7 @@ static int enqueue_search(tc_engine *e, int num_sims, double cpuct)
     }
     for (int s = 0; s < num_sims; ++s)
         for (int h = 0; h < e->n_halves; ++h)
-            TC_TRY(enqueue_simulation(e, cpuct, h, h == 0 ? e->stream : e->side_stream[h - 1]));
+            TC_TRY(enqueue_simulation(e, cpuct, h, h == 0 ? e->stream : e->side_stream[h - 1], s == 0, s == num_sims - 1));
     for (int h = 1; h < e->n_halves; ++h) {
         TC_CUDA(cudaEventRecord(e->ev_join[h - 1], e->side_stream[h - 1]));
         TC_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join[h - 1], 0));

@@ -243,11 +243,8 @@ struct EdgeRegs {     // one edge as held by its lane during selection
 // One simulation's descent for every tree: mcts.py:243-325 (selection part of `_search`).
 // Every level costs one dependent memory round trip: the lanes load the whole edge block (priors, values,
 // counts and where each child lives), Ns is the warp sum of the counts, the arg-max lane broadcasts the child.
-__global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
+__device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree, const int lane, const double cpuct)
 {
-    const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (tree >= ts.E) return;
     TreeCtl *cp = ts.ctl + tree;
     Walk w;
     w.active = cp->active;
@@ -484,11 +481,8 @@ __device__ __forceinline__ double numpy_sum81(const double x[3], int lane)
 }
 
 // Expansion of the evaluated leaf (mcts.py:268-290) and backup along the path (mcts.py:327-341).
-__global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
+__device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const int tree, const int lane)
 {
-    int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (tree >= ts.E) return;
     const TreeCtl *cp = ts.ctl + tree;
     int kind = cp->leaf_kind;
     if (kind == LEAF_NONE) return;
@@ -541,6 +535,32 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
         eb.Q[j] = q;
         eb.N[j] = cnt + 1u;
     }
+}
+
+__global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
+{
+    const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tree >= ts.E) return;
+    select_tree(ts, tree, threadIdx.x & 31, cpuct);
+}
+
+__global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
+{
+    const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tree >= ts.E) return;
+    expand_backup_tree(ts, tree, threadIdx.x & 31);
+}
+
+// Backup of simulation k and descent of simulation k+1 in one launch: the warp that owns the tree finishes the
+// expansion/backup, then walks down again while the path's nodes are still in cache.
+__global__ void __launch_bounds__(128, 7) k_backup_select(TreeStore ts, double cpuct)
+{
+    const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tree >= ts.E) return;
+    const int lane = threadIdx.x & 31;
+    expand_backup_tree(ts, tree, lane);
+    __syncwarp();          // the lanes' writes to the edge records are ordered before the descent's reads
+    select_tree(ts, tree, lane, cpuct);
 }
 
 // Deterministic evaluator, specification in oracle/evaluators.py (HashEvaluator)
@@ -639,6 +659,11 @@ void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uin
 void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st)
 {
     k_select<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, cpuct);
+}
+
+void launch_backup_select(const TreeStore &ts, double cpuct, cudaStream_t st)
+{
+    k_backup_select<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, cpuct);
 }
 
 void launch_expand_backup(const TreeStore &ts, cudaStream_t st)

@@ -99,6 +99,7 @@ void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uin
 void launch_reset(const TreeStore &ts, int env, cudaStream_t st);
 void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st);
 void launch_expand_backup(const TreeStore &ts, cudaStream_t st);
+void launch_backup_select(const TreeStore &ts, double cpuct, cudaStream_t st);
 void launch_hash_eval(const TreeStore &ts, HashEvalParams hp, cudaStream_t st);
 void launch_root_counts(const TreeStore &ts, uint32_t *counts_dev, double *q_dev, cudaStream_t st);
 void launch_pack_fields(int n, const uint16_t *board, const uint16_t *occ, const int8_t *last, uint32_t *out,
