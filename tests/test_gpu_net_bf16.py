@@ -58,9 +58,10 @@ def torch_default_state_dict(seed, channels, blocks, emb):
     for k, w in sd.items():
         if k.endswith("num_batches_tracked"):
             continue
-        if k.endswith("running_mean") or (k.endswith(".bias") and (".1." in k or "bn" in k)):
+        is_bn = k.rsplit(".", 1)[0] + ".running_mean" in sd
+        if k.endswith("running_mean") or (k.endswith(".bias") and is_bn):
             sd[k] = np.zeros_like(w)
-        elif k.endswith("running_var") or (k.endswith(".weight") and (".1." in k or "bn" in k)):
+        elif k.endswith("running_var") or (k.endswith(".weight") and is_bn):
             sd[k] = np.ones_like(w)
         else:
             layer = k.rsplit(".", 1)[0] + ".weight"
@@ -76,10 +77,12 @@ def test_bf16_large_batch_and_ragged_sizes():
     eng.load_weights(sd)
     rng = np.random.RandomState(1)
     x = (rng.random_sample((2048, 4, 9, 9)) < 0.3).astype(np.float32)
-    pi, v = eng.forward(x, BF16)
-    rpi, rv = resnet_oracle.forward(sd, x)
+    pi, v, logits = eng.forward(x, BF16, want_logits=True)
+    rpi, rv, rlogits = resnet_oracle.forward(sd, x, return_logits=True)
     assert np.abs(pi - rpi.numpy()).max() < TOL_BF16 and np.abs(v - rv.numpy().ravel()).max() < TOL_BF16
-    for b in (1, 2, 77, 129, 1000):
+    assert np.abs(logits - rlogits.numpy()).max() < TOL_BF16          # probabilities are near-uniform at this init
+    assert rpi.numpy().max() < 0.5                                    # not a saturated soft-max
+    for b in (1, 2, 77, 129, 1000, 1333, 1480, 1776, 1924):       # group sizes 1..13 positions per CTA
         p1, v1 = eng.forward(x[:b], BF16)
         assert np.array_equal(p1, pi[:b]) and np.array_equal(v1, v[:b])      # rows are independent of the batch
 
@@ -117,3 +120,22 @@ def test_search_with_bf16_evaluator():
     assert (counts.sum(1) == 63).all() and (counts == counts[0]).all()
     st = eng.stats()
     assert st["nn_leaves"] + st["terminal_leaves"] == 512 * 64
+
+
+@pytest.mark.parametrize("arch", [(32, 3, 256), (16, 4, 256), (64, 2, 128)])
+def test_opt_in_dx_trunk_matches_fp32_reference(arch, monkeypatch):
+    """The 3C-column formulation of the fused trunk (nn_fused_dx.cu, TACULT_FUSED_DX=1) is opt-in; it must meet the
+    same 2e-2 bar, for batch sizes that give 1..13 positions per CTA."""
+    monkeypatch.setenv("TACULT_FUSED_DX", "1")          # read when the weights are uploaded
+    sd = torch_default_state_dict(7, *arch)
+    eng = tb.Engine(2048, 2)
+    eng.load_weights(sd)
+    rng = np.random.RandomState(3)
+    x = (rng.random_sample((2048, 4, 9, 9)) < 0.3).astype(np.float32)
+    pi, v, logits = eng.forward(x, BF16, want_logits=True)
+    rpi, rv, rlogits = resnet_oracle.forward(sd, x, return_logits=True)
+    assert np.abs(pi - rpi.numpy()).max() < TOL_BF16 and np.abs(v - rv.numpy().ravel()).max() < TOL_BF16
+    assert np.abs(logits - rlogits.numpy()).max() < TOL_BF16
+    for b in (1, 150, 1333, 1924):
+        p1, v1 = eng.forward(x[:b], BF16)
+        assert np.array_equal(p1, pi[:b]) and np.array_equal(v1, v[:b])
