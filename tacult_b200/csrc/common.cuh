@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/tacult_b200.h"
@@ -73,7 +74,7 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // Optional per-kernel-class timing with CUDA events on the launching stream (tc_profile_*).
 struct Profiler {
     bool on = false;
-    struct Span { int cls; cudaEvent_t a, b; };
+    struct Span { int cls; cudaEvent_t a, b; cudaStream_t st; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> pool;
     cudaEvent_t open_a = nullptr;
@@ -97,12 +98,23 @@ struct Profiler {
         if (!on || open_cls < 0) return;
         cudaEvent_t b = get();
         cudaEventRecord(b, st);
-        spans.push_back({open_cls, open_a, b});
+        spans.push_back({open_cls, open_a, b, st});
         open_cls = -1;
     }
     // sums elapsed ms / launches per class and recycles the events; call after a stream synchronise
     void collect(double *ms, unsigned long long *launches, int n_cls)
     {
+        if (getenv("TACULT_TRACE") && spans.size() >= 64) {
+            // start / duration of the last launches on each stream, relative to a common origin (overlap picture)
+            const size_t first = spans.size() - 64;
+            for (size_t i = first; i < spans.size(); ++i) {
+                float t0 = 0.f, dt = 0.f;
+                cudaEventElapsedTime(&t0, spans[first].a, spans[i].a);
+                cudaEventElapsedTime(&dt, spans[i].a, spans[i].b);
+                fprintf(stderr, "[trace] stream %p class %d start %8.1f us dur %6.1f us\n", (void *)spans[i].st, spans[i].cls,
+                        t0 * 1e3f, dt * 1e3f);
+            }
+        }
         for (auto &s : spans) {
             float t = 0.f;
             cudaEventElapsedTime(&t, s.a, s.b);

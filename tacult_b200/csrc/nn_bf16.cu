@@ -513,6 +513,7 @@ struct NetBF16Impl {
     CUtensorMap map_dx_stem, map_dx_conv, map_dx_bias;
     std::vector<CUtensorMap> map_conv_w;
     int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
+    size_t side_smem_budget = 96 * 1024;       // what an fc1 / heads CTA may use next to a resident fused-trunk CTA
     int sm_count = SM_COUNT;
 };
 
@@ -649,8 +650,18 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
         int G = 0, T = 0;
         m.fused = m.stem_on_tensor && (!fz || atoi(fz) != 0) && fused_plan(C, G, T);
         if (m.fused) {
-            m.fused_G = G;          // maxima; the kernel balances its groups from the live leaf count
+            // G, T are the largest group that fits.  Size the kernel for THIS instance's capacity instead: the group the
+            // kernel would pick for a full batch (it re-balances from the live leaf count, never above these maxima), so
+            // that the shared memory left on each SM lets the fc1 / heads CTAs of the other partition co-reside with a
+            // trunk CTA instead of queueing behind the whole trunk grid.
+            const char *gz = getenv("TACULT_FUSED_GMAX");
+            if (gz && atoi(gz) > 0) G = std::min(G, atoi(gz));
+            const int waves = std::max(1, (cap + m.sm_count * G - 1) / (m.sm_count * G));
+            G = std::max(1, std::min(G, (cap + m.sm_count * waves - 1) / (m.sm_count * waves)));
+            T = (100 * G + 127) / 128;
+            m.fused_G = G;
             m.fused_T = T;
+            m.side_smem_budget = (size_t)227 * 1024 - fused_smem_bytes(C, T) - 2048;
             std::vector<__nv_bfloat16> wall(std::max<size_t>(1, L) * 9 * C * C);
             std::vector<float> ball((1 + L) * (size_t)C);
             for (int c = 0; c < C; ++c) ball[c] = f.stem_b[c];
@@ -690,7 +701,7 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     }
     const size_t budget = 200 * 1024;
     m.conv_stages = pick_stages(m.block_k, C, C <= 64 ? 48 * 1024 : budget);
-    m.fc1_stages = pick_stages(64, m.fc1_block_n, m.fc1_block_n > 64 ? 200 * 1024 : 96 * 1024);
+    m.fc1_stages = pick_stages(64, m.fc1_block_n, m.fc1_block_n > 64 ? 200 * 1024 : std::min<size_t>(96 * 1024, m.side_smem_budget));
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
@@ -872,7 +883,7 @@ int NetBF16::forward(int batch, const int *count_dev, const uint32_t *states, co
         H.n_blocks = 1;
         H.a_row0 = 0;
         H.b_tap_rows = 0;
-        H.stages = pick_stages(64, 96, 96 * 1024);
+        H.stages = pick_stages(64, 96, std::min<size_t>(96 * 1024, m.side_smem_budget));
         H.mode = OUT_HEADS;
         H.ldc = 81;
         H.bias = m.head_b96.p;

@@ -102,13 +102,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     const int rows = LEAD + 128 * P.T + 16;
     const int buf_bytes = (rows * SW + 1023) & ~1023;
     uint8_t *X = smem, *Y = smem + buf_bytes;
-    uint8_t *W = smem + 2 * buf_bytes;                          // 9 taps of the current layer
-    uint8_t *Bt = W + 9 * W_TAP;                                // bias tile of the current layer
-    uint8_t *Id = Bt + WS_TAP;                                  // identity [C x C]
+    constexpr int W_BUF = 9 * W_TAP + WS_TAP;                   // 9 taps + the bias tile of one layer
+    uint8_t *W = smem + 2 * buf_bytes;                          // two layers' weights: layer n lives in buffer n & 1
+    uint8_t *Id = W + 2 * W_BUF;                                // identity [C x C]
     uint8_t *Ones = Id + W_TAP;                                 // 128 rows x 16 ones
     uint64_t *bars = reinterpret_cast<uint64_t *>(Ones + 4096);
-    uint64_t *tdone = bars, *wfull = bars + MAX_TILES, *wfree = bars + MAX_TILES + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + MAX_TILES + 2);
+    uint64_t *tdone = bars;                                     // [t]: the UMMAs of tile t have completed
+    // [layer & 1][t]: the epilogue of tile t has written its activations.  Two banks, because a parity wait must never
+    // fall two phases behind: a neighbouring tile may run a whole layer ahead of the issuer that waits on it, not two.
+    uint64_t *aready = bars + MAX_TILES;
+    uint64_t *wfull = bars + 3 * MAX_TILES, *wfree = bars + 3 * MAX_TILES + 2;      // [2] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * MAX_TILES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int count = P.batch;
@@ -126,8 +130,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
 
     if (threadIdx.x == 0) {
         for (int t = 0; t < MAX_TILES; ++t) mbar_init(tdone + t, 1);
-        mbar_init(wfull, 1);
-        mbar_init(wfree, (uint32_t)issuers);
+        for (int t = 0; t < 2 * MAX_TILES; ++t) mbar_init(aready + t, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, (uint32_t)issuers); }
         fence_barrier_init();
         tma_prefetch_desc(&tmW_stem);
         tma_prefetch_desc(&tmW_conv);
@@ -154,11 +158,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     if (warp == 0 && lane == 0 && (int)blockIdx.x < n_groups) {
         mbar_expect_tx(wfull, 10u * C * 32u);
         for (int tap = 0; tap < 9; ++tap) tma_load_2d(W + tap * WS_TAP, &tmW_stem, wfull, 0, tap * C);
-        tma_load_2d(Bt, &tmBias, wfull, 0, 0);
+        tma_load_2d(W + 9 * W_TAP, &tmBias, wfull, 0, 0);
     }
 
-    const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y), w_addr = smem_u32(W);
-    const uint64_t ones_desc = desc_of<32>(smem_u32(Ones)), bias_desc = desc_of<32>(smem_u32(Bt));
+    const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y);
+    const uint64_t ones_desc = desc_of<32>(smem_u32(Ones));
     const uint32_t id_addr = smem_u32(Id);
     const uint32_t idesc = make_instr_desc(C);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
@@ -206,10 +210,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
         }
         __syncthreads();
 
+        // Layers are NOT separated by a block-wide barrier: tile t of layer l+1 only needs the activations of tiles
+        // t-1, t, t+1 of layer l (taps reach 11 rows), so its UMMAs start as soon as those three epilogues have
+        // arrived on aready[], while the tail of layer l is still draining.  Weights are double buffered.
         for (int l = 0; l < n_layers; ++l, ++lcount) {
-            const uint32_t ph = lcount & 1u;
+            const uint32_t ph = lcount & 1u;                    // tdone / aready complete once per layer
+            const uint32_t wb = lcount & 1u, wph = (lcount >> 1) & 1u;      // weight buffer of this layer and its phase
             const bool stamp = P.timeline && blockIdx.x == 0 && group == (int)blockIdx.x && lane == 0;
-            if (stamp && warp == 1) P.timeline[8 * l + 0] = clock64();
             // layer 0: planes(Y) -> X;  odd l (first conv of a block): X -> Y;  even l > 0: Y -> X, + residual X
             const bool to_y = (l & 1) != 0;
             const uint32_t s_addr = to_y ? x_addr : y_addr;
@@ -218,32 +225,51 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
             const bool residual = l > 0 && !to_y;
             if (warp == 0) {
                 if (lane == 0) {
-                    // once this layer's UMMAs have consumed the weights, stream in the next layer's
-                    mbar_wait(wfree, ph);
+                    // stream the NEXT layer's weights into the other buffer once the layer before this one (its
+                    // previous user) has been consumed by the tensor pipe
                     const bool more_layers = l + 1 < n_layers;
                     const bool more_groups = group + (int)gridDim.x < n_groups;
-                    if (more_layers) {
-                        mbar_expect_tx(wfull, 9u * C * (uint32_t)SW + C * 32u);
-                        for (int tap = 0; tap < 9; ++tap)
-                            tma_load_2d(W + tap * W_TAP, &tmW_conv, wfull, 0, (l * 9 + tap) * C);
-                        tma_load_2d(Bt, &tmBias, wfull, 0, (l + 1) * C);
-                    } else if (more_groups) {
-                        mbar_expect_tx(wfull, 10u * C * 32u);
-                        for (int tap = 0; tap < 9; ++tap) tma_load_2d(W + tap * WS_TAP, &tmW_stem, wfull, 0, tap * C);
-                        tma_load_2d(Bt, &tmBias, wfull, 0, 0);
+                    if (more_layers || more_groups) {
+                        const uint32_t nb = wb ^ 1u;
+                        uint8_t *Wn = W + nb * W_BUF;
+                        if (lcount >= 1) mbar_wait(wfree + nb, ((lcount - 1) >> 1) & 1u);
+                        if (more_layers) {
+                            mbar_expect_tx(wfull + nb, 9u * C * (uint32_t)SW + C * 32u);
+                            for (int tap = 0; tap < 9; ++tap)
+                                tma_load_2d(Wn + tap * W_TAP, &tmW_conv, wfull + nb, 0, (l * 9 + tap) * C);
+                            tma_load_2d(Wn + 9 * W_TAP, &tmBias, wfull + nb, 0, (l + 1) * C);
+                        } else {
+                            mbar_expect_tx(wfull + nb, 10u * C * 32u);
+                            for (int tap = 0; tap < 9; ++tap)
+                                tma_load_2d(Wn + tap * WS_TAP, &tmW_stem, wfull + nb, 0, tap * C);
+                            tma_load_2d(Wn + 9 * W_TAP, &tmBias, wfull + nb, 0, 0);
+                        }
                     }
                 }
             } else if (warp <= ISSUERS) {
                 const int e = warp - 1;
                 // ===== issue the UMMAs of this warp's tiles (warp-uniform code, one elected lane issues) =====
                 if (e < issuers) {
-                    mbar_wait(wfull, ph);
+                    if (stamp && warp == 1) P.timeline[8 * l + 0] = clock64();
+                    mbar_wait(wfull + wb, wph);
                     tc_fence_after();
                     if (stamp && warp == 1) P.timeline[8 * l + 1] = clock64();
                     if (elect_one()) {
+                        const uint32_t w_addr = smem_u32(W + wb * W_BUF);
+                        const uint64_t bias_desc = desc_of<32>(w_addr + 9 * W_TAP);
                         // tile by tile, so that a finished tile's epilogue overlaps the UMMAs of the next ones; the four
                         // issuers keep four independent accumulators in flight on the tensor pipe
                         for (int t = e; t < T; t += ISSUERS) {
+                            if (l > 0) {
+                                // inputs of this tile: the previous layer's rows of tiles t-1, t, t+1 (and the
+                                // accumulator columns of tile t, drained by the same epilogue)
+                                uint64_t *prev = aready + ((lcount - 1) & 1u) * MAX_TILES;
+                                const uint32_t pph = ((lcount - 1) >> 1) & 1u;
+                                if (t > 0) mbar_wait(prev + t - 1, pph);
+                                mbar_wait(prev + t, pph);
+                                if (t + 1 < T) mbar_wait(prev + t + 1, pph);
+                                tc_fence_after();
+                            }
                             const uint32_t d_tmem = tmem_base + (uint32_t)(t * C);
                             const uint32_t a_tile = s_addr + (uint32_t)((LEAD + 128 * t) * SW);
                             umma_bf16(d_tmem, ones_desc, bias_desc, idesc, 0u);      // accumulator starts as the bias
@@ -268,7 +294,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                             }
                             umma_commit(tdone + t);
                         }
-                        umma_commit(wfree);
+                        umma_commit(wfree + wb);
                     }
                     __syncwarp();
                     if (stamp && warp == 1) P.timeline[8 * l + 2] = clock64();
@@ -308,16 +334,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                             }
                         }
                     }
+                    // the rows are written through the generic proxy and read by the next layer's UMMAs (async proxy);
+                    // the accumulator columns are free again as well
+                    tc_fence_before();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(aready + wb * MAX_TILES + t);
                 }
                 if (stamp && warp == 1 + ISSUERS) P.timeline[8 * l + 4] = clock64();
-                fence_async_smem();       // activations written through the generic proxy feed the next layer's UMMAs
-                if (stamp && warp == 1 + ISSUERS) P.timeline[8 * l + 5] = clock64();
             }
-            tc_fence_before();
-            __syncthreads();
-            tc_fence_after();
-            if (stamp && warp == 1) P.timeline[8 * l + 6] = clock64();
         }
+        // group boundary: the next group's planes overwrite Y and its stem overwrites the accumulators
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
     }
     tc_fence_before();
     __syncthreads();
@@ -327,14 +357,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-static size_t fused_smem_bytes(int C, int T)
+size_t fused_smem_bytes(int C, int T)
 {
     const size_t SW = 2 * C;
     const size_t rows = LEAD + 128 * T + 16;
     const size_t buf = (rows * SW + 1023) & ~(size_t)1023;
     const size_t wtap = (C * SW + 1023) & ~(size_t)1023;
     const size_t wstap = (C * 32 + 1023) & ~(size_t)1023;
-    return 1024 + 2 * buf + 9 * wtap + wstap + wtap + 4096 + (MAX_TILES + 2) * 8 + 16;
+    return 1024 + 2 * buf + 2 * (9 * wtap + wstap) + wtap + 4096 + (3 * MAX_TILES + 4) * 8 + 16;
 }
 
 bool fused_plan(int C, int &G, int &T)
@@ -397,12 +427,10 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
         long long h[8 * 64];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, timeline_dev, sizeof h, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[fused timeline] layer: start->weights  issue  first-tile-done  epilogue  fence  barrier (cycles)\n");
+        fprintf(stderr, "[fused timeline] layer: issuer-0 start | weights ready | issued | first tile done | epilogues done (cycles since layer 0 start)\n");
         for (int l = 0; l <= n_conv; ++l)
-            fprintf(stderr, "[fused timeline] %2d: %6lld %6lld %6lld %6lld %6lld %6lld | total %6lld\n", l,
-                    h[8 * l + 1] - h[8 * l], h[8 * l + 2] - h[8 * l + 1], h[8 * l + 3] - h[8 * l + 2],
-                    h[8 * l + 4] - h[8 * l + 3], h[8 * l + 5] - h[8 * l + 4], h[8 * l + 6] - h[8 * l + 5],
-                    h[8 * l + 6] - h[8 * l]);
+            fprintf(stderr, "[fused timeline] %2d: %7lld %7lld %7lld %7lld %7lld\n", l, h[8 * l] - h[0], h[8 * l + 1] - h[0],
+                    h[8 * l + 2] - h[0], h[8 * l + 3] - h[0], h[8 * l + 4] - h[0]);
     }
     return TC_OK;
 }

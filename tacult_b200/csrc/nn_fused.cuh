@@ -11,6 +11,7 @@ namespace tc {
 
 // largest tile count T (and positions per group G) that fits shared memory and TMEM for C channels
 bool fused_plan(int C, int &G, int &T);
+size_t fused_smem_bytes(int C, int T);            // dynamic shared memory of k_trunk_fused for T tiles per group
 void fused_bias_tiles(const std::vector<float> &bias_all, std::vector<__nv_bfloat16> &out);
 int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_conv, const CUtensorMap &bias_tiles, int G,
                        int T, int n_conv, int in_planes, int batch, const int *count_dev, const uint32_t *states,

@@ -24,10 +24,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// A wait that never completes would hang the GPU until the driver resets it: after ~2 s of polling the kernel traps
+// instead, which surfaces as a CUDA error (loud) at the next API call.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
     const uint32_t addr = smem_u32(bar);
+    uint32_t polls = 0;
+    long long t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -36,6 +40,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "=r"(ok)
             : "r"(addr), "r"(parity)
             : "memory");
+        if (!ok && (++polls & 0xFFFu) == 0) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000ll) __trap();
+        }
     } while (!ok);
 }
 __device__ __forceinline__ void fence_barrier_init()
