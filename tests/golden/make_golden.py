@@ -244,11 +244,49 @@ def gen_callers(ref, name):
     print(name, "arena", arena_rows, "coach examples", len(ref_ex))
 
 
+def gen_learner(ref, name, ckpt_name):
+    """Three optimisation steps of the LIVE reference learner (NNetWrapper.training_step, nn_wrapper.py:45-56) on a
+    tiny net with drop-out active, and the checkpoint it then writes (nn_wrapper.py:138-163)."""
+    import shutil
+    import tempfile
+    torch.manual_seed(11)
+    net = ref.network._UtacNNet(cuda=False, dropout=0.2, channels=8, num_residual_blocks=1, embedding_size=32)
+    init = {k: v.detach().clone().numpy() for k, v in net.state_dict().items()}
+    args = ref.utils.dotdict({"cuda": False, "lr": 1e-3, "epochs": 1, "steps_per_epoch": 3, "numIters": 1,
+                              "num_warm_restarts": 1})
+    wrapper = ref.nn_wrapper.NNetWrapper(net, args)
+    rng = np.random.RandomState(12)
+    steps, batch = 3, 16
+    obs = (rng.random_sample((steps, batch, 4, 9, 9)) < 0.3).astype(np.float32)
+    pis = rng.random_sample((steps, batch, 81)).astype(np.float32) ** 4
+    pis /= pis.sum(axis=2, keepdims=True)
+    vs = rng.choice(np.array([-1.0, 1.0, 1e-4], dtype=np.float32), size=(steps, batch))
+    net.train()
+    torch.manual_seed(5)                   # drop-out masks
+    losses = [wrapper.training_step(torch.from_numpy(obs[i]), torch.from_numpy(pis[i]), torch.from_numpy(vs[i]))
+              for i in range(steps)]
+    final = {k: v.detach().clone().numpy() for k, v in net.state_dict().items()}
+    net.eval()
+    with torch.no_grad():
+        epi, ev = net(torch.from_numpy(obs[0]))
+    tmp = tempfile.mkdtemp()
+    wrapper.save_checkpoint(folder=tmp, filename="ref.pt")
+    shutil.copy(os.path.join(tmp, "ref.pt"), os.path.join(HERE, ckpt_name))
+    shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(HERE, name), obs=obs, pis=pis, vs=vs, losses=np.array(losses, dtype=np.float64),
+                        eval_pi=epi.numpy(), eval_v=ev.numpy(), keys=np.array(list(init.keys())),
+                        **{"init/" + k: v for k, v in init.items()}, **{"final/" + k: v for k, v in final.items()})
+    print(name, "losses", losses, "checkpoint bytes", os.path.getsize(os.path.join(HERE, ckpt_name)))
+
+
 def main():
     import logging
     logging.disable(logging.ERROR)   # the zero-prior fallback logs an error per hit (mcts.py:281)
     ref = ref_loader.load_reference()
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "learner":      # regenerate only the learner fixtures
+        gen_learner(ref, "learner_steps.npz", "ref_checkpoint_tiny.pt")
+        return
     gen_rules("rules_playouts.npz")
     gen_callers(ref, "callers.npz")
     gen_symmetries(ref, "symmetries.npz")
@@ -262,6 +300,7 @@ def main():
     gen_mcts_selfplay(ref, "mcts_selfplay_c1.npz", salt=21, pi_levels=0, v_levels=0, sims=25, envs=8, cpuct=1.0, seed=5)
     gen_mcts_arena(ref, "mcts_arena_2sims.npz", salts=(11, 12), sims=2, envs=8, cpuct=2.4, seed=6)
     gen_mcts_arena(ref, "mcts_arena_16sims.npz", salts=(13, 14), sims=16, envs=4, cpuct=2.4, seed=7)
+    gen_learner(ref, "learner_steps.npz", "ref_checkpoint_tiny.pt")
 
 
 if __name__ == "__main__":

@@ -32,3 +32,29 @@ def test_selfplay_examples_with_gpu_engine(golden, make_args):
     ex = selfplay_with(gpu_mcts, make_args)
     assert len(ex) == int(g["coach_examples"])
     assert (examples_digest(ex) == g["coach_sha256"]).all()
+
+
+def test_packed_arena_matches_reference_results(golden):
+    """The native two-engine arena on packed positions (tacult_b200/arena.py) against the results the LIVE reference
+    arena produced with the same evaluators and seeds: same counts -> same RNG draws -> same games."""
+    from tacult_b200.arena import PackedArena
+    for seed, one, two, draws in golden("callers.npz")["arena"]:
+        np.random.seed(int(seed))
+        e1 = tb.Engine(6, 4096)
+        e2 = tb.Engine(6, 4096)
+        e1.set_hash_evaluator(1)
+        e2.set_hash_evaluator(2)
+        arena = PackedArena(e1, e2, num_sims=3, cpuct=2.4)
+        assert arena.play_games(20) == (one, two, draws)
+        assert arena.sims > 0 and len(arena.ply_seconds) > 0
+
+
+def test_packed_arena_lowest_index_mode_is_deterministic():
+    from tacult_b200.arena import PackedArena
+    results = []
+    for _ in range(2):
+        e1, e2 = tb.Engine(32, 4096), tb.Engine(32, 4096)
+        e1.set_hash_evaluator(3)
+        e2.set_hash_evaluator(4)
+        results.append(PackedArena(e1, e2, num_sims=8, cpuct=2.4, tie_break="lowest").play_games(64))
+    assert results[0] == results[1] and sum(results[0]) == 64
