@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "../../include/tacult_b200.h"
@@ -72,6 +73,35 @@ struct DevBuf {                     // RAII device allocation
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (tc_profile_*).
+// Programmatic dependent launch: a kernel launched with this attribute may start (and run its prologue) while the
+// previous kernel in the stream is still draining; it must call griddep_wait() before it reads anything the previous
+// kernels wrote and before it writes anything they may still read.  The wait returns once every prerequisite grid has
+// completed and its memory is visible; in a normally launched kernel it is a no-op.  No kernel here triggers its
+// dependents early: waiting CTAs would hold shared memory the other partition's kernels need.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled()
+{
+    static const int on = [] { const char *v = getenv("TACULT_PDL"); return v ? atoi(v) : 1; }();
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 struct Profiler {
     bool on = false;
     struct Span { int cls; cudaEvent_t a, b; cudaStream_t st; };

@@ -196,7 +196,7 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     TC_ALLOC(e->eval_state, 8 * E);
     TC_ALLOC(e->eval_pi, 81 * E);
     TC_ALLOC(e->eval_v, E);
-    TC_ALLOC(e->eval_count, 4);
+    TC_ALLOC(e->eval_count, 8);          // a pair per partition: simulation s counts its leaves in [s & 1]
     TC_ALLOC(e->error_flag, 1);
     TC_ALLOC(e->root_states, 8 * E);
     TC_ALLOC(e->root_active, E);
@@ -253,7 +253,7 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
             v.eval_state = ts.eval_state + 8 * t0;
             v.eval_pi = ts.eval_pi + 81 * t0;
             v.eval_v = ts.eval_v + t0;
-            v.eval_count = ts.eval_count + h;
+            v.eval_count = ts.eval_count + 2 * h;
             e->hts[h] = v;
         }
         if (e->n_halves > 1) {
@@ -269,7 +269,7 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     }
     cudaMemsetAsync(e->ctl.p, 0, e->ctl.bytes(), e->stream);
     cudaMemsetAsync(e->error_flag.p, 0, sizeof(int), e->stream);
-    cudaMemsetAsync(e->eval_count.p, 0, 4 * sizeof(int), e->stream);
+    cudaMemsetAsync(e->eval_count.p, 0, 8 * sizeof(int), e->stream);
     cudaMemsetAsync(e->log_count.p, 0, sizeof(int), e->stream);
     cudaMemsetAsync(e->root_active.p, 0, e->root_active.bytes(), e->stream);
     launch_reset(ts, -1, e->stream);
@@ -372,12 +372,18 @@ extern "C" int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, co
 // One lock-step simulation for every tree of part `h`: select -> evaluate leaves -> expand + backup.
 // Inside a run of simulations the backup of simulation k and the descent of simulation k+1 share a launch
 // (`first` = no pending backup, `last` = no following descent).
-static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st, bool first, bool last)
+static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st, int sim, bool last)
 {
-    const TreeStore &ts = e->hts[h];
+    // leaf counter: simulation `sim` counts in slot sim & 1 of the partition's pair; its descent kernel zeroes the other
+    // slot for simulation sim + 1, so no memset node sits between the kernels of the chain (they are launched with
+    // programmatic stream serialisation, common.cuh)
+    TreeStore ts = e->hts[h];
+    int *pair = ts.eval_count;
+    ts.eval_count = pair + (sim & 1);
+    ts.eval_count_next = pair + ((sim + 1) & 1);
+    const bool first = sim == 0;
     NetF32 &n32 = h == 0 ? e->net32 : e->net32x[h - 1];
     NetBF16 &n16 = h == 0 ? e->net16 : e->net16x[h - 1];
-    TC_CUDA(cudaMemsetAsync(ts.eval_count, 0, sizeof(int), st));
     e->prof.begin(TC_K_SELECT, st);
     if (first) launch_select(ts, cpuct, st);
     else launch_backup_select(ts, cpuct, st);
@@ -414,13 +420,14 @@ static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st
 static int enqueue_search(tc_engine *e, int num_sims, double cpuct)
 {
     if (num_sims <= 0) return TC_OK;
+    TC_CUDA(cudaMemsetAsync(e->eval_count.p, 0, 8 * sizeof(int), e->stream));      // slot 0 of every pair for simulation 0
     if (e->n_halves > 1) {
         TC_CUDA(cudaEventRecord(e->ev_fork, e->stream));
         for (int h = 1; h < e->n_halves; ++h) TC_CUDA(cudaStreamWaitEvent(e->side_stream[h - 1], e->ev_fork, 0));
     }
     for (int s = 0; s < num_sims; ++s)
         for (int h = 0; h < e->n_halves; ++h)
-            TC_TRY(enqueue_simulation(e, cpuct, h, h == 0 ? e->stream : e->side_stream[h - 1], s == 0, s == num_sims - 1));
+            TC_TRY(enqueue_simulation(e, cpuct, h, h == 0 ? e->stream : e->side_stream[h - 1], s, s == num_sims - 1));
     for (int h = 1; h < e->n_halves; ++h) {
         TC_CUDA(cudaEventRecord(e->ev_join[h - 1], e->side_stream[h - 1]));
         TC_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join[h - 1], 0));

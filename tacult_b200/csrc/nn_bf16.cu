@@ -89,10 +89,6 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int count = live_count(P.count_dev, P.batch);
-    const int m_total = count * P.rows_per_unit;
-    const int m_tiles = (m_total + 127) >> 7;
-    const int n_tiles = m_tiles * P.n_blocks;
     const int num_kb = P.taps * P.k_chunks;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * P.block_n) tmem_cols <<= 1;
@@ -110,6 +106,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above overlaps the tail of the previous kernel in the stream; its outputs (the live count, the A
+    // operand) are only touched from here on
+    griddep_wait();
+    const int count = live_count(P.count_dev, P.batch);
+    const int m_total = count * P.rows_per_unit;
+    const int m_tiles = (m_total + 127) >> 7;
+    const int n_tiles = m_tiles * P.n_blocks;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -741,10 +744,10 @@ static void launch_gemm(const NetBF16Impl &m, int block_k, const CUtensorMap &a,
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(max_tiles, m.sm_count * per_sm);
     if (grid < 1) grid = 1;
-    if (P.mode == OUT_HEADS) k_gemm_tc<64, true><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
-    else if (block_k == 64) k_gemm_tc<64, false><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
-    else if (block_k == 32) k_gemm_tc<32, false><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
-    else k_gemm_tc<16, false><<<grid, GEMM_THREADS, smem, st>>>(a, b, P);
+    if (P.mode == OUT_HEADS) launch_chain(k_gemm_tc<64, true>, grid, GEMM_THREADS, smem, st, a, b, P);
+    else if (block_k == 64) launch_chain(k_gemm_tc<64, false>, grid, GEMM_THREADS, smem, st, a, b, P);
+    else if (block_k == 32) launch_chain(k_gemm_tc<32, false>, grid, GEMM_THREADS, smem, st, a, b, P);
+    else launch_chain(k_gemm_tc<16, false>, grid, GEMM_THREADS, smem, st, a, b, P);
 }
 
 void launch_heads_f32(int batch, const int *count_dev, int E, const float *emb, const float *W, const float *bias,

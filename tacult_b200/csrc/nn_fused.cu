@@ -115,24 +115,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * MAX_TILES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int count = P.batch;
-    if (P.count_dev) count = min(count, *P.count_dev);
-    // group size chosen from the LIVE count so that the persistent grid is evenly loaded (P.G / P.T are the maxima
-    // the shared-memory carve-up was sized for)
-    const int waves = max(1, (count + (int)gridDim.x * P.G - 1) / ((int)gridDim.x * P.G));
-    const int G = max(1, min(P.G, (count + (int)gridDim.x * waves - 1) / ((int)gridDim.x * waves)));
-    const int T = (100 * G + 127) / 128;
-    const int n_groups = (count + G - 1) / G;
     const int n_layers = 1 + P.n_conv;
-    const int issuers = min(ISSUERS, T);
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < P.T * C) tmem_cols <<= 1;
 
+    // ---- prologue that depends on nothing the previous kernel wrote: it overlaps that kernel's tail (programmatic
+    //      dependent launch, common.cuh) ----
     if (threadIdx.x == 0) {
-        for (int t = 0; t < MAX_TILES; ++t) mbar_init(tdone + t, 1);
-        for (int t = 0; t < 2 * MAX_TILES; ++t) mbar_init(aready + t, 4);
-        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, (uint32_t)issuers); }
-        fence_barrier_init();
         tma_prefetch_desc(&tmW_stem);
         tma_prefetch_desc(&tmW_conv);
         tma_prefetch_desc(&tmBias);
@@ -144,6 +133,24 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     for (int i = threadIdx.x; i < W_TAP / 16; i += FUSED_THREADS) reinterpret_cast<uint4 *>(Id)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < 4096 / 16; i += FUSED_THREADS)
         reinterpret_cast<uint4 *>(Ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+
+    // ---- from here on the leaf count and the leaf positions written by the descent kernel are read ----
+    griddep_wait();
+    int count = P.batch;
+    if (P.count_dev) count = min(count, *P.count_dev);
+    // group size chosen from the LIVE count so that the persistent grid is evenly loaded (P.G / P.T are the maxima
+    // the shared-memory carve-up was sized for)
+    const int waves = max(1, (count + (int)gridDim.x * P.G - 1) / ((int)gridDim.x * P.G));
+    const int G = max(1, min(P.G, (count + (int)gridDim.x * waves - 1) / ((int)gridDim.x * waves)));
+    const int T = (100 * G + 127) / 128;
+    const int n_groups = (count + G - 1) / G;
+    const int issuers = min(ISSUERS, T);
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < MAX_TILES; ++t) mbar_init(tdone + t, 1);
+        for (int t = 0; t < 2 * MAX_TILES; ++t) mbar_init(aready + t, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, (uint32_t)issuers); }
+        fence_barrier_init();
+    }
     __syncthreads();
     if (threadIdx.x < C)            // identity, K-major rows of SW bytes in the swizzle pattern
         *reinterpret_cast<__nv_bfloat16 *>(Id + swz<SW>((uint32_t)threadIdx.x * SW + (uint32_t)threadIdx.x * 2u)) =
@@ -415,13 +422,13 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
     const int grid = std::max(1, std::min(batch, sm_count));     // the kernel sizes its groups from the live count
     if (C == 16) {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trunk_fused<16><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
+        TC_CUDA(launch_chain(k_trunk_fused<16>, grid, FUSED_THREADS, smem, st, w_stem, w_conv, bias_tiles, P));
     } else if (C == 32) {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trunk_fused<32><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
+        TC_CUDA(launch_chain(k_trunk_fused<32>, grid, FUSED_THREADS, smem, st, w_stem, w_conv, bias_tiles, P));
     } else {
         TC_CUDA(cudaFuncSetAttribute(k_trunk_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_trunk_fused<64><<<grid, FUSED_THREADS, smem, st>>>(w_stem, w_conv, bias_tiles, P);
+        TC_CUDA(launch_chain(k_trunk_fused<64>, grid, FUSED_THREADS, smem, st, w_stem, w_conv, bias_tiles, P));
     }
     if (P.timeline) {
         long long h[8 * 64];

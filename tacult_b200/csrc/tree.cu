@@ -539,6 +539,8 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
 
 __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
 {
+    griddep_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ts.eval_count_next) *ts.eval_count_next = 0;
     const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (tree >= ts.E) return;
     select_tree(ts, tree, threadIdx.x & 31, cpuct);
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
 
 __global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
 {
+    griddep_wait();
     const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (tree >= ts.E) return;
     expand_backup_tree(ts, tree, threadIdx.x & 31);
@@ -555,6 +558,10 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
 // expansion/backup, then walks down again while the path's nodes are still in cache.
 __global__ void __launch_bounds__(128, 7) k_backup_select(TreeStore ts, double cpuct)
 {
+    griddep_wait();
+    // the other counter of the pair was last read by the evaluator kernels of the previous simulation, which have
+    // completed; the next simulation's descent starts counting from zero without a memset node in the stream
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ts.eval_count_next) *ts.eval_count_next = 0;
     const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (tree >= ts.E) return;
     const int lane = threadIdx.x & 31;
@@ -566,6 +573,7 @@ __global__ void __launch_bounds__(128, 7) k_backup_select(TreeStore ts, double c
 // Deterministic evaluator, specification in oracle/evaluators.py (HashEvaluator)
 __global__ void k_hash_eval(TreeStore ts, HashEvalParams hp)
 {
+    griddep_wait();
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= *ts.eval_count) return;
@@ -658,22 +666,22 @@ void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uin
 
 void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st)
 {
-    k_select<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, cpuct);
+    launch_chain(k_select, warp_grid(ts.E, 128), 128, 0, st, ts, cpuct);
 }
 
 void launch_backup_select(const TreeStore &ts, double cpuct, cudaStream_t st)
 {
-    k_backup_select<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, cpuct);
+    launch_chain(k_backup_select, warp_grid(ts.E, 128), 128, 0, st, ts, cpuct);
 }
 
 void launch_expand_backup(const TreeStore &ts, cudaStream_t st)
 {
-    k_expand_backup<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts);
+    launch_chain(k_expand_backup, warp_grid(ts.E, 128), 128, 0, st, ts);
 }
 
 void launch_hash_eval(const TreeStore &ts, HashEvalParams hp, cudaStream_t st)
 {
-    k_hash_eval<<<warp_grid(ts.E, 256), 256, 0, st>>>(ts, hp);
+    launch_chain(k_hash_eval, warp_grid(ts.E, 256), 256, 0, st, ts, hp);
 }
 
 void launch_root_counts(const TreeStore &ts, uint32_t *counts_dev, double *q_dev, cudaStream_t st)

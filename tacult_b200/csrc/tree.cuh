@@ -63,6 +63,7 @@ struct TreeStore {
     float *eval_pi;          // [E][81]
     float *eval_v;           // [E]
     int *eval_count;
+    int *eval_count_next;       // counter of the NEXT simulation, zeroed by this one's descent kernel (or null)
     int *error_flag;
 };
 
