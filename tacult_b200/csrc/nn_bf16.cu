@@ -209,6 +209,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
         int as = 0;
         uint32_t aphase = 0;
+        // HEADS: when every CTA has at most one tile the operand ring is idle once the accumulator is complete, and
+        // its first 41 KB stage the soft-max rows for coalesced stores (alignment: row0 * 81 * 4 is a multiple of 16
+        // because row0 is a multiple of 32)
+        float *stage_rows = (HEADS && (int)gridDim.x >= n_tiles && !P.out_logits && 128 * 81 * 4 <= P.stages * stage_bytes)
+                                ? reinterpret_cast<float *>(stage0) : nullptr;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int mt = tile / P.n_blocks, nb = tile - mt * P.n_blocks;
             const int n0 = nb * P.block_n;
@@ -258,10 +263,35 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(const __grid_constant_
                         sum += lg[j];
                     }
                     const float inv = 1.f / sum;
-                    float *po = reinterpret_cast<float *>(P.out) + out_row * 81;
-#pragma unroll
-                    for (int j = 0; j < 81; ++j) po[j] = lg[j] * inv;
                     P.out_v[out_row] = tanhf(lg[81]);
+                    if (stage_rows) {
+                        // row-strided 4-byte stores cost one LSU transaction per lane (measured: the store queue was
+                        // the epilogue's main stall); go through shared memory and write the warp's 32 x 81 block,
+                        // which is contiguous in the output, with 16-byte coalesced stores.  Pitch 81 words is odd,
+                        // so the column-wise writes are conflict-free.
+                        float *sr = stage_rows + (32 * quarter + lane) * 81;
+#pragma unroll
+                        for (int j = 0; j < 81; ++j) sr[j] = lg[j] * inv;
+                    } else {
+                        float *po = reinterpret_cast<float *>(P.out) + out_row * 81;
+#pragma unroll
+                        for (int j = 0; j < 81; ++j) po[j] = lg[j] * inv;
+                    }
+                }
+                if (stage_rows) {
+                    __syncwarp();
+                    const int row0 = 128 * mt + 32 * quarter;
+                    const int n_rows = min(32, m_total - row0);
+                    if (n_rows > 0) {
+                        const float4 *src = reinterpret_cast<const float4 *>(stage_rows + 32 * quarter * 81);
+                        float4 *dstp = reinterpret_cast<float4 *>(reinterpret_cast<float *>(P.out) + (size_t)row0 * 81);
+                        const int n4 = n_rows * 81 / 4;          // 32 rows x 81 words = 648 float4; ragged tails below
+                        for (int i = lane; i < n4; i += 32) dstp[i] = src[i];
+                        const float *s1 = stage_rows + 32 * quarter * 81;
+                        float *d1 = reinterpret_cast<float *>(P.out) + (size_t)row0 * 81;
+                        for (int i = 4 * n4 + lane; i < n_rows * 81; i += 32) d1[i] = s1[i];
+                    }
+                    __syncwarp();
                 }
             } else {
             const int cw = P.block_n < 32 ? 16 : 32;
