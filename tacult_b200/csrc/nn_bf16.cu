@@ -546,6 +546,7 @@ struct NetBF16Impl {
     CUtensorMap map_dx_stem, map_dx_conv, map_dx_bias;
     std::vector<CUtensorMap> map_conv_w;
     int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
+    bool fc1_split_k = true;               // K split over a CTA pair (nn_fc1.cu); TACULT_FC1_SPLITK=0 disables
     size_t side_smem_budget = 96 * 1024;       // what an fc1 / heads CTA may use next to a resident fused-trunk CTA
     int sm_count = SM_COUNT;
 };
@@ -574,7 +575,7 @@ static int upload(DevBuf<T> &dst, const std::vector<T> &src)
     return TC_OK;
 }
 
-static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
+static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_sm)
 {
     m.d = f.d;
     m.capacity = cap;
@@ -674,6 +675,8 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
         const char *fb = getenv("TACULT_FC1_BLOCK_N");
         m.fc1_block_n = E % 64 == 0 ? 64 : (E % 32 == 0 ? 32 : 16);
         if (fb && atoi(fb) > 0 && E % atoi(fb) == 0 && atoi(fb) % 32 == 0 && atoi(fb) <= 256) m.fc1_block_n = atoi(fb);
+        const char *sk = getenv("TACULT_FC1_SPLITK");
+        m.fc1_split_k = !sk || atoi(sk) != 0;
     }
     TC_TRY(make_map(&m.map_flat, m.flat.p, (uint64_t)flat_rows, (uint64_t)81 * C, 128, 64));
     TC_TRY(make_map(&m.map_fc1, m.fc1_w.p, (uint64_t)E, (uint64_t)81 * C, (uint32_t)m.fc1_block_n, 64));
@@ -694,7 +697,9 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
             T = (100 * G + 127) / 128;
             m.fused_G = G;
             m.fused_T = T;
-            m.side_smem_budget = (size_t)227 * 1024 - fused_smem_bytes(C, T) - 2048;
+            // only an instance that shares the SMs with other partitions' kernels limits its fc1 / heads CTAs to the
+            // shared memory a trunk CTA leaves free
+            if (share_sm) m.side_smem_budget = (size_t)227 * 1024 - fused_smem_bytes(C, T) - 2048;
             std::vector<__nv_bfloat16> wall(std::max<size_t>(1, L) * 9 * C * C);
             std::vector<float> ball((1 + L) * (size_t)C);
             for (int c = 0; c < C; ++c) ball[c] = f.stem_b[c];
@@ -742,7 +747,7 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap)
     return TC_OK;
 }
 
-int NetBF16::upload(const FoldedNet &f, int capacity)
+int NetBF16::upload(const FoldedNet &f, int capacity, bool share_sm)
 {
     loaded = false;
     const int C = f.d.channels, E = f.d.embedding_size;
@@ -751,7 +756,7 @@ int NetBF16::upload(const FoldedNet &f, int capacity)
     if (((size_t)81 * C * 2) % 16 != 0) { why_not = "fc1 row pitch must be a multiple of 16 bytes"; return TC_OK; }
     delete impl;
     impl = new NetBF16Impl();
-    int rc = upload_impl(*impl, f, capacity);
+    int rc = upload_impl(*impl, f, capacity, share_sm);
     if (rc != TC_OK) {
         why_not = tc_last_error();
         delete impl;
@@ -902,7 +907,10 @@ int NetBF16::forward(int batch, const int *count_dev, const uint32_t *states, co
     P.residual = nullptr;
     P.out = m.heads_on_tensor ? (void *)m.emb16.p : (void *)m.emb.p;
     prof->begin(TC_K_NN_FC1, st);
-    launch_gemm(m, 64, m.map_flat, m.map_fc1, P, ((batch + 127) / 128) * P.n_blocks, st);
+    if (m.fc1_split_k && m.heads_on_tensor && m.fc1_block_n == 64)
+        TC_TRY(launch_fc1_splitk(m.map_flat, m.map_fc1, batch, count_dev, 81 * C, E, m.fc1_stages, m.fc1_b.p, m.emb16.p, st));
+    else
+        launch_gemm(m, 64, m.map_flat, m.map_fc1, P, ((batch + 127) / 128) * P.n_blocks, st);
     prof->end(st);
     prof->begin(TC_K_NN_HEADS, st);
     if (m.heads_on_tensor) {

@@ -3,6 +3,9 @@
 #pragma once
 #include <string>
 
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "nn.cuh"
 
 namespace tc {
@@ -18,11 +21,18 @@ struct NetBF16 {
     NetBF16 &operator=(const NetBF16 &) = delete;
     ~NetBF16();
     // returns TC_OK and sets `loaded`, or leaves loaded == false with the reason in why_not
-    int upload(const FoldedNet &f, int capacity);
+    // share_sm: other partitions' kernels run next to this instance's (limits fc1 / heads shared memory)
+    int upload(const FoldedNet &f, int capacity, bool share_sm = false);
     // same contract as NetF32::forward; returns the number of kernels launched or a negative TC_E* code
     int forward(int batch, const int *count_dev, const uint32_t *states, const float *obs, float *pi, float *v,
                 float *logits, cudaStream_t st, Profiler *prof = nullptr);
 };
+
+// fc1 with K split over a cluster of two CTAs (nn_fc1.cu); a = activations [rows][K] (box 128 x 64), b = weights [E][K]
+// (box 64 x 64), out = bf16 embedding [rows][E] with bias and ReLU applied
+size_t fc1_splitk_smem(int stages);
+int launch_fc1_splitk(const CUtensorMap &a, const CUtensorMap &b, int batch, const int *count_dev, int K, int E, int stages,
+                      const float *bias, __nv_bfloat16 *out, cudaStream_t st);
 
 int debug_trunk_bf16(NetBF16 &net, int batch, const uint32_t *states_dev, int n_convs, float *out_dev, cudaStream_t st);
 

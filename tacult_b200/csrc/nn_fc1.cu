@@ -1,0 +1,215 @@
+// fc1 (81*C -> E) with the reduction dimension split over a pair of CTAs (thread-block cluster of 2).
+//
+// Why: at self-play batch sizes fc1 is latency-bound, not bandwidth- or math-bound.  A [128 x 64] output tile streams
+// 81*C/64 operand chunks of 24 KB through a ring that the shared-memory budget (a fused-trunk CTA of the other
+// partition lives on the same SM) limits to 3 stages; with ~1.3 us per L2 round trip that is ~14 round trips per CTA
+// (ncu: 23 us for 1024 rows, tensor pipe 15 % active, one CTA on 32..64 of the 148 SMs).  Splitting K over two CTAs
+// doubles the bytes in flight and the SMs in use and halves the chain of round trips.  The partial accumulator of the
+// second CTA goes to the first one through distributed shared memory (st.shared::cluster into the first CTA's idle
+// operand ring), which adds bias, ReLU, packs to bf16 and stores the embedding rows.
+#include <algorithm>
+
+#include "nn_bf16.cuh"
+#include "tcgen05.cuh"
+
+namespace tc {
+
+namespace fc1 {
+
+constexpr int THREADS = 192;             // warp 0: TMA producer, warp 1: UMMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int BLOCK_N = 64, BLOCK_K = 64, SW = 128;
+constexpr int A_BYTES = 128 * SW, B_BYTES = BLOCK_N * SW, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int MAX_STAGES = 8;
+
+struct Params {
+    const int *count_dev;
+    int batch;
+    int num_kb;              // ceil(81*C / 64)
+    int n_blocks;            // E / 64
+    int stages;
+    int ldc;                 // E
+    const float *bias;
+    __nv_bfloat16 *out;      // [row][E]
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, uint32_t bits)
+{
+    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS) k_fc1_splitk(const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmB, Params P)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)P.stages * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + MAX_STAGES, *tfull = bars + 2 * MAX_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();                                       // the trunk's output and the live count are read from here on
+
+    int count = P.batch;
+    if (P.count_dev) count = min(count, *P.count_dev);
+    const int n_tiles = ((count + 127) >> 7) * P.n_blocks;
+    const int tile = blockIdx.x >> 1;                     // both CTAs of a cluster share the output tile
+    const uint32_t rank = cluster_ctarank();
+    if (tile < n_tiles) {                                 // uniform over the cluster
+        const int mt = tile / P.n_blocks, nb = tile - mt * P.n_blocks;
+        const int half = (P.num_kb + 1) >> 1;
+        const int kb0 = rank ? half : 0, kb1 = rank ? P.num_kb : half;
+        uint32_t a0[32], a1[32];                          // this thread's accumulator row (epilogue warps)
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    uint8_t *sa = smem + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(full + stage, (uint32_t)STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, full + stage, kb * BLOCK_K, 128 * mt);
+                    tma_load_2d(sa + A_BYTES, &tmB, full + stage, kb * BLOCK_K, nb * BLOCK_N);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = make_instr_desc(BLOCK_N);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        umma_bf16(tmem_base, make_smem_desc<SW>(a_addr + 32 * k), make_smem_desc<SW>(b_addr + 32 * k), idesc,
+                                  (uint32_t)((kb != kb0) | k));
+                    umma_commit(empty + stage);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull);
+            }
+        } else {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+            tmem_ld32(t_base, a0);
+            tmem_ld32(t_base + 32u, a1);
+            tmem_ld_wait();
+            tc_fence_before();
+        }
+        __syncwarp();
+        // (1) both accumulators are in registers and CTA 0's operand ring is drained (its epilogue warps have seen tfull)
+        cluster_sync_all();
+        const int quarter = warp & 3;
+        const int r = 32 * quarter + lane;                // row inside the tile
+        float *part = reinterpret_cast<float *>(smem);    // [64 columns][128 rows] in CTA 0
+        if (warp >= 2 && rank == 1) {
+            const uint32_t remote = map_to_cta(smem_u32(part), 0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                st_cluster_f32(remote + (uint32_t)((j * 128 + r) * 4), a0[j]);
+                st_cluster_f32(remote + (uint32_t)(((32 + j) * 128 + r) * 4), a1[j]);
+            }
+        }
+        // (2) the partial sums have landed in CTA 0
+        cluster_sync_all();
+        if (warp >= 2 && rank == 0) {
+            const int q = 128 * mt + r;
+            if (q < count) {
+                const float *bias = P.bias + nb * BLOCK_N;
+                __nv_bfloat16 *o = P.out + (size_t)q * P.ldc + nb * BLOCK_N;
+#pragma unroll
+                for (int j = 0; j < 64; j += 8) {
+                    uint4 ov;
+                    __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int c = j + 2 * t;
+                        const float x0 = __uint_as_float(c < 32 ? a0[c] : a1[c - 32]) + part[c * 128 + r] + __ldg(bias + c);
+                        const float x1 = __uint_as_float(c + 1 < 32 ? a0[c + 1] : a1[c + 1 - 32]) + part[(c + 1) * 128 + r] +
+                                         __ldg(bias + c + 1);
+                        op[t] = __floats2bfloat162_rn(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+                    }
+                    *reinterpret_cast<uint4 *>(o + j) = ov;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+}  // namespace fc1
+
+size_t fc1_splitk_smem(int stages) { return 1024 + (size_t)stages * fc1::STAGE_BYTES + (2 * fc1::MAX_STAGES + 2) * 8 + 16; }
+
+int launch_fc1_splitk(const CUtensorMap &a, const CUtensorMap &b, int batch, const int *count_dev, int K, int E, int stages,
+                      const float *bias, __nv_bfloat16 *out, cudaStream_t st)
+{
+    fc1::Params P{};
+    P.count_dev = count_dev;
+    P.batch = batch;
+    P.num_kb = (K + fc1::BLOCK_K - 1) / fc1::BLOCK_K;
+    P.n_blocks = E / fc1::BLOCK_N;
+    P.stages = stages;
+    P.ldc = E;
+    P.bias = bias;
+    P.out = out;
+    const size_t smem = fc1_splitk_smem(stages);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TC_CUDA(cudaFuncSetAttribute(fc1::k_fc1_splitk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ((batch + 127) / 128) * P.n_blocks);
+    cfg.blockDim = dim3(fc1::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    TC_CUDA(cudaLaunchKernelEx(&cfg, fc1::k_fc1_splitk, a, b, P));
+    return TC_OK;
+}
+
+}  // namespace tc
