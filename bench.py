@@ -341,11 +341,14 @@ def roofline(prof, k0, k1, a, evaluator, flops_eval):
     # trunk = conv_in + the residual-block convolutions (one fused launch for this net): SURVEY.md §8d trunk term
     trunk_flops_per_leaf = 2.0 * 81 * 9 * NET["channels"] * (4 + 2 * NET["num_residual_blocks"] * NET["channels"])
     conv_flops = trunk_flops_per_leaf * d["nn_leaves"]
+    # the backup of simulation k and the descent of simulation k+1 share one launch (class "select"); the separate
+    # expand_backup launch only closes the last simulation of a move, so the tree-side bytes are attributed together
+    tree_ms = kernels.get("select", {}).get("ms", 0.0) + kernels.get("expand_backup", {}).get("ms", 0.0)
     if "select" in kernels:
-        kernels["select"].update(bound="hbm", achieved=sel_bytes / (kernels["select"]["ms"] * 1e-3) / 1e9, unit="GB/s")
+        kernels["select"].update(bound="hbm", achieved=(sel_bytes + exp_bytes) / (tree_ms * 1e-3) / 1e9, unit="GB/s",
+                                 note="descent + fused backup/expansion of the previous simulation")
     if "expand_backup" in kernels:
-        kernels["expand_backup"].update(bound="hbm", achieved=exp_bytes / (kernels["expand_backup"]["ms"] * 1e-3) / 1e9,
-                                        unit="GB/s")
+        kernels["expand_backup"].update(bound="hbm", note="last simulation of a move only; bytes counted under select")
     if "nn_conv" in kernels:
         kernels["nn_conv"].update(bound="tensor", achieved=conv_flops / (kernels["nn_conv"]["ms"] * 1e-3) / 1e12,
                                   unit="TFLOP/s")
