@@ -740,6 +740,8 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
     const size_t budget = 200 * 1024;
     m.conv_stages = pick_stages(m.block_k, C, C <= 64 ? 48 * 1024 : budget);
     m.fc1_stages = pick_stages(64, m.fc1_block_n, m.fc1_block_n > 64 ? 200 * 1024 : std::min<size_t>(96 * 1024, m.side_smem_budget));
+    if (const char *fs = getenv("TACULT_FC1_STAGES"))
+        if (atoi(fs) >= 2 && atoi(fs) <= MAX_STAGES) m.fc1_stages = atoi(fs);
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     TC_CUDA(cudaFuncSetAttribute(k_gemm_tc<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
