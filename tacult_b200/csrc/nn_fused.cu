@@ -13,10 +13,14 @@
 // Everything linear is done by the tensor pipe, so the epilogue is only ReLU + bf16 pack + store:
 //   bias      = one K=16 UMMA  (all-ones A tile) x (bias split in bf16 hi+lo on two K slots)
 //   residual  = C/16 UMMAs     (block input X, unshifted) x (identity tile)
-// With N = C a UMMA is only a few cycles of tensor work, so a single issuing thread cannot keep the pipe busy
-// (measured: ~130 cycles per issue).  Eight worker warps therefore each issue the UMMAs of their own tiles
-// (one elected lane, descriptors kept in uniform registers) and then run the epilogue of tile quarters.
-// Warp 0 streams the next layer's weights with TMA while the current layer computes.
+// (adding the bias in the epilogue instead was measured 12 % slower, presumably because its shared-memory reads compete with the UMMA
+// operand fetches, and the L1TEX/smem data path is this kernel's busiest unit - 76 % in ncu.)
+// A UMMA with N = C is only a few cycles of tensor work but costs ~45-55 cycles end to end, so one issuing thread
+// cannot keep the pipe busy: four issuer warps (one elected lane each, descriptors in uniform registers) issue the
+// UMMAs of tiles t = i (mod 4), eight epilogue warps (two per TMEM lane quarter) drain the accumulators, and warp 0
+// streams the NEXT layer's weights into the other half of a double buffer with TMA.  Layers are not separated by a
+// block-wide barrier: tile t of layer l+1 starts as soon as the epilogues of tiles t-1, t, t+1 of layer l have arrived
+// on per-tile mbarriers (two banks, see below).  The prologue overlaps the previous kernel's tail (griddep_wait).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
