@@ -147,6 +147,30 @@ def test_full_size_properties():
     assert st["max_nodes_one_tree"] <= 200
 
 
+@pytest.mark.parametrize("parts", ["2", "3", "4"])
+def test_partitioned_engine_gives_the_same_counts(parts, monkeypatch):
+    """TACULT_HALVES splits the trees over streams (read at tc_create); the trees are independent, so every root count
+    and Q must equal the single-partition engine's, for different positions per tree and a ragged last partition."""
+    n = 600
+    rng = np.random.RandomState(11)
+    res = tb.rules_playouts(5, 0, n, max_plies=12)           # distinct mid-game roots
+    roots = np.array([list(r.final_state) for r in res], dtype=np.uint32)
+    active = (rng.random_sample(n) < 0.9).astype(np.uint8)
+
+    def run():
+        eng = tb.Engine(n, 40 * 4 + 64, hash_salt=17)
+        eng.set_roots_packed(roots, active)
+        eng.search(40, 2.4)
+        return eng.root_counts(), eng.root_q()
+
+    monkeypatch.setenv("TACULT_HALVES", "1")
+    c1, q1 = run()
+    monkeypatch.setenv("TACULT_HALVES", parts)
+    c2, q2 = run()
+    assert np.array_equal(c1, c2) and np.array_equal(q1.view(np.uint64), q2.view(np.uint64))
+    assert (c1[active == 0] == 0).all() and c1[active == 1].sum() > 0
+
+
 def test_record_replay_with_network_evaluator(make_args):
     """Identical evaluator outputs, real network: the engine logs every leaf (state, pi, v) its fp32 ResNet
     produced; the oracle search replays those exact float32 values and must reach the same visit counts."""
