@@ -122,11 +122,12 @@ def test_search_with_bf16_evaluator():
     assert st["nn_leaves"] + st["terminal_leaves"] == 512 * 64
 
 
+@pytest.mark.parametrize("switch", ["TACULT_FUSED_DX", "TACULT_FUSED_P16"])
 @pytest.mark.parametrize("arch", [(32, 3, 256), (16, 4, 256), (64, 2, 128)])
-def test_opt_in_dx_trunk_matches_fp32_reference(arch, monkeypatch):
-    """The 3C-column formulation of the fused trunk (nn_fused_dx.cu, TACULT_FUSED_DX=1) is opt-in; it must meet the
-    same 2e-2 bar, for batch sizes that give 1..13 positions per CTA."""
-    monkeypatch.setenv("TACULT_FUSED_DX", "1")          # read when the weights are uploaded
+def test_opt_in_trunk_formulations_match_fp32_reference(arch, switch, monkeypatch):
+    """The two stacked-dx formulations of the fused trunk (nn_fused_dx.cu, nn_fused_p16.cu) are opt-in experiments;
+    they must meet the same 2e-2 bar, for batch sizes that give every group size.  (64 channels: p16 falls back.)"""
+    monkeypatch.setenv(switch, "1")          # read when the weights are uploaded
     sd = torch_default_state_dict(7, *arch)
     eng = tb.Engine(2048, 2)
     eng.load_weights(sd)
