@@ -142,17 +142,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     griddep_wait();
     int count = P.batch;
     if (P.count_dev) count = min(count, *P.count_dev);
-    // group size chosen from the LIVE count so that the persistent grid is evenly loaded (P.G / P.T are the maxima
-    // the shared-memory carve-up was sized for)
-    const int waves = max(1, (count + (int)gridDim.x * P.G - 1) / ((int)gridDim.x * P.G));
-    const int G = max(1, min(P.G, (count + (int)gridDim.x * waves - 1) / ((int)gridDim.x * waves)));
-    const int T = (100 * G + 127) / 128;
-    const int n_groups = (count + G - 1) / G;
-    const int issuers = min(ISSUERS, T);
+    // The live positions are dealt out evenly: CTA b owns positions [b * per, (b + 1) * per) and walks them in groups of
+    // P.G (the largest group the shared-memory carve-up holds) plus one smaller remainder group, which costs fewer 128-row
+    // tiles than equal groups (21 positions: 14 + 7 -> 11 + 6 tiles, against 11 + 11 -> 9 + 9).
+    const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int p_begin = min(count, (int)blockIdx.x * per), p_end = min(count, p_begin + per);
+    const int n_my_groups = (p_end - p_begin + P.G - 1) / P.G;
     if (threadIdx.x == 0) {
         for (int t = 0; t < MAX_TILES; ++t) mbar_init(tdone + t, 1);
         for (int t = 0; t < 2 * MAX_TILES; ++t) mbar_init(aready + t, 4);
-        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, (uint32_t)issuers); }
+        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, (uint32_t)ISSUERS); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
 
     uint32_t lcount = 0;       // layers executed so far by this CTA (mbarrier phase = lcount & 1)
-    if (warp == 0 && lane == 0 && (int)blockIdx.x < n_groups) {
+    if (warp == 0 && lane == 0 && n_my_groups > 0) {
         mbar_expect_tx(wfull, 10u * C * 32u);
         for (int tap = 0; tap < 9; ++tap) tma_load_2d(W + tap * WS_TAP, &tmW_stem, wfull, 0, tap * C);
         tma_load_2d(W + 9 * W_TAP, &tmBias, wfull, 0, 0);
@@ -178,8 +177,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     const uint32_t idesc = make_instr_desc(C);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 
-    for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
-        const int pos0 = group * G;
+    for (int group = 0; group < n_my_groups; ++group) {
+        const int pos0 = p_begin + group * P.G;
+        const int G = min(P.G, p_end - pos0);
+        const int T = (100 * G + 127) / 128;
         // ---- observation planes of the group -> channels 0..15 of the group's rows in Y (activation layout:
         //      the stem's UMMAs read K = 16 of it; pad rows are never touched and stay zero) ----
         if (warp > ISSUERS) {
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
         for (int l = 0; l < n_layers; ++l, ++lcount) {
             const uint32_t ph = lcount & 1u;                    // tdone / aready complete once per layer
             const uint32_t wb = lcount & 1u, wph = (lcount >> 1) & 1u;      // weight buffer of this layer and its phase
-            const bool stamp = P.timeline && blockIdx.x == 0 && group == (int)blockIdx.x && lane == 0;
+            const bool stamp = P.timeline && blockIdx.x == 0 && group == 0 && lane == 0;
             // layer 0: planes(Y) -> X;  odd l (first conv of a block): X -> Y;  even l > 0: Y -> X, + residual X
             const bool to_y = (l & 1) != 0;
             const uint32_t s_addr = to_y ? x_addr : y_addr;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                     // stream the NEXT layer's weights into the other buffer once the layer before this one (its
                     // previous user) has been consumed by the tensor pipe
                     const bool more_layers = l + 1 < n_layers;
-                    const bool more_groups = group + (int)gridDim.x < n_groups;
+                    const bool more_groups = group + 1 < n_my_groups;
                     if (more_layers || more_groups) {
                         const uint32_t nb = wb ^ 1u;
                         uint8_t *Wn = W + nb * W_BUF;
@@ -259,8 +260,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
                 }
             } else if (warp <= ISSUERS) {
                 const int e = warp - 1;
-                // ===== issue the UMMAs of this warp's tiles (warp-uniform code, one elected lane issues) =====
-                if (e < issuers) {
+                // ===== issue the UMMAs of this warp's tiles (warp-uniform code, one elected lane issues); an issuer without
+                //       a tile in this group still waits for the layer's weights and releases them, so that the arrivals
+                //       of two layers can never mix on a wfree barrier =====
+                {
                     if (stamp && warp == 1) P.timeline[8 * l + 0] = clock64();
                     mbar_wait(wfull + wb, wph);
                     tc_fence_after();
