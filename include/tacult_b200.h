@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TC_ABI_VERSION 1
+#define TC_ABI_VERSION 2
 #define TC_ACTIONS 81
 #define TC_STATE_WORDS 8
 
@@ -117,6 +117,31 @@ typedef struct {
     int32_t outcome;
 } tc_playout_result;
 int tc_rules_playouts(uint64_t seed, uint64_t first_game, int n, int max_plies, tc_playout_result *out_host);
+
+/* ---- host-side game-state object: utac_gym.core.GameState / utac_gym.core.types.GAMESTATE (external C++ `utac`
+ *      behind nanobind in the reference; surface inferred from the call sites).  Plain host
+ *      functions on a caller-owned struct, no device involved: the reference keeps these objects on the host too.
+ *      board = stones of player +1, occ = all stones, side = player to move (+1 / -1), last_square = cell of the
+ *      last move (-1 at game start); main_board / main_occ / game_occ are derived (utac_game.py:222-229). ---------- */
+typedef struct {
+    uint16_t board[9];           /* GAMESTATE.board  (utac_game.py:101-103) */
+    uint16_t occ[9];             /* GAMESTATE.occ */
+    uint16_t main_board;         /* sub-boards won by player +1 (utac_game.py:104) */
+    uint16_t main_occ;           /* sub-boards won by either player */
+    uint16_t game_occ;           /* sub-boards closed: won or full */
+    int8_t side;                 /* utac_game.py:105-106 */
+    int8_t last_square;          /* utac_game.py:182-184,215-216 */
+} tc_gamestate;
+void tc_gs_init(tc_gamestate *s);                                  /* GameState()            utac_game.py:18 */
+void tc_gs_rederive(tc_gamestate *s);                              /* GameState(GAMESTATE)   utac_game.py:107,218 */
+int  tc_gs_make_move(tc_gamestate *s, int action);                 /* .make_move             utac_game.py:46; TC_EILLEGAL */
+int  tc_gs_valid_mask(const tc_gamestate *s, double *mask81);      /* .get_valid_mask        utac_game.py:62; returns #legal */
+int  tc_gs_is_terminal(const tc_gamestate *s);                     /* .is_terminal           utac_game.py:75 */
+int  tc_gs_terminal_value(const tc_gamestate *s);                  /* .terminal_value        utac_game.py:78,81 */
+void tc_gs_obs(const tc_gamestate *s, float *obs324);              /* .get_obs               utac_game.py:248, base/utils.py:8 */
+/* the canonicalBoards list of getActionProbs (mcts.py:175) -> packed roots in one call; active[i] == 0 on entry marks a
+ * None board (mcts.py:235-239); finished boards whose side is not +1 (arena.py:176-184) come back inactive */
+int  tc_gs_pack(int n, const tc_gamestate *gs_host, uint32_t *states_host, uint8_t *active_host);
 
 /* ---- search engine: replaces VectorizedMCTS (/root/reference/src/tacult/base/mcts.py:147-358) ---- */
 int tc_create(const tc_config *cfg, tc_engine **out);              /* VectorizedMCTS.__init__ mcts.py:152-162 */
@@ -214,6 +239,13 @@ int tc_selfplay_get_stats(tc_engine *e, tc_selfplay_stats *out);
 /* copies finished-game records to the host (or leaves them on the device for NCCL): returns count */
 int tc_selfplay_drain(tc_engine *e, int max, tc_example *out_host, int *count_out);
 int tc_selfplay_drain_dev(tc_engine *e, int max, tc_example *out_dev, int *count_out);
+/* Trajectory records -> training examples on the device: what coach.py:136-149 builds on the host — the eight dihedral
+ * images of (obs, pi) in getSymmetries' order (utac_game.py:109-220: for i in 0..3, for flip in (False, True)), pi from
+ * the counts (tau = 1) or the one-hot of the move played (tau = 0, mcts.py:206-213), z = z_sign (x 1e-4 for a draw).
+ * Example j of a record array of n_records is image j % 8 of record j / 8.  Output row r holds example index_dev[r]
+ * (index_dev == NULL: r itself): obs[n_out][4][9][9], pi[n_out][81], z[n_out], all float32 device buffers. */
+int tc_examples_from_records_dev(tc_engine *e, int n_out, const tc_example *records_dev, int n_records,
+                                 const int32_t *index_dev, float *obs_dev, float *pi_dev, float *z_dev);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libtacult_b200.so")
 
+ABI_VERSION = 2
 TC_OK, TC_EINVAL, TC_ECUDA, TC_ECAPACITY, TC_ESTATE, TC_EILLEGAL = 0, -1, -2, -3, -4, -5
 EVAL_NET_F32, EVAL_NET_BF16, EVAL_HASH = 0, 1, 2
 LIVE, LOST, DRAW, WON = 0, 1, 2, 3
@@ -66,6 +67,24 @@ class PlayoutResult(ctypes.Structure):
     ]
 
 
+class GameStateStruct(ctypes.Structure):
+    """tc_gamestate: the GAMESTATE members (utac_game.py:101-106,176-216,241), 44 bytes."""
+    _fields_ = [
+        ("board", ctypes.c_uint16 * 9),
+        ("occ", ctypes.c_uint16 * 9),
+        ("main_board", ctypes.c_uint16),
+        ("main_occ", ctypes.c_uint16),
+        ("game_occ", ctypes.c_uint16),
+        ("side", ctypes.c_int8),
+        ("last_square", ctypes.c_int8),
+    ]
+
+
+GAMESTATE_DTYPE = np.dtype([("board", "<u2", (9,)), ("occ", "<u2", (9,)), ("main_board", "<u2"), ("main_occ", "<u2"),
+                            ("game_occ", "<u2"), ("side", "i1"), ("last_square", "i1")])
+assert GAMESTATE_DTYPE.itemsize == ctypes.sizeof(GameStateStruct) == 44
+
+
 class SelfPlayConfig(ctypes.Structure):
     _fields_ = [
         ("num_sims", ctypes.c_int32),
@@ -96,10 +115,19 @@ EXAMPLE_DTYPE = np.dtype({
 # every symbol include/tacult_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _u64, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_double, ctypes.c_size_t
 _pi = ctypes.POINTER(ctypes.c_int)
+_gsp = ctypes.POINTER(GameStateStruct)
 SYMBOLS = {
     "tc_abi_version": (_i, []),
     "tc_last_error": (ctypes.c_char_p, []),
     "tc_device_memory": (_i, [_i, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "tc_gs_init": (None, [_gsp]),
+    "tc_gs_rederive": (None, [_gsp]),
+    "tc_gs_make_move": (_i, [_gsp, _i]),
+    "tc_gs_valid_mask": (_i, [_gsp, _vp]),
+    "tc_gs_is_terminal": (_i, [_gsp]),
+    "tc_gs_terminal_value": (_i, [_gsp]),
+    "tc_gs_obs": (None, [_gsp, _vp]),
+    "tc_gs_pack": (_i, [_i, _vp, _vp, _vp]),
     "tc_rules_step": (_i, [_i, _vp, _vp, _vp, _vp]),
     "tc_rules_legal_mask": (_i, [_i, _vp, _vp]),
     "tc_rules_status": (_i, [_i, _vp, _vp]),
@@ -134,6 +162,7 @@ SYMBOLS = {
     "tc_selfplay_get_stats": (_i, [_vp, ctypes.POINTER(SelfPlayStats)]),
     "tc_selfplay_drain": (_i, [_vp, _i, _vp, _pi]),
     "tc_selfplay_drain_dev": (_i, [_vp, _i, _vp, _pi]),
+    "tc_examples_from_records_dev": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -153,8 +182,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = the .so does not match the header
         fn.restype = res
         fn.argtypes = args
-    if lib.tc_abi_version() != 1:
-        raise ImportError(f"ABI mismatch: library reports version {lib.tc_abi_version()}, binding expects 1")
+    if lib.tc_abi_version() != ABI_VERSION:
+        raise ImportError(f"ABI mismatch: library reports version {lib.tc_abi_version()}, binding expects {ABI_VERSION}")
     _lib = lib
     return lib
 

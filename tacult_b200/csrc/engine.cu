@@ -243,6 +243,8 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
             const int want = atoi(hv);
             e->n_halves = (want >= 1 && want <= 4 && E >= want) ? want : 1;
         }
+        // the evaluation log is appended in stream order: one partition only, or log_count would race across streams
+        if (cfg->eval_log_capacity > 0) e->n_halves = 1;
         // partition sizes are multiples of 32 trees: per-partition row blocks of the leaf buffers stay 16-byte aligned
         const int per = (((int)((E + e->n_halves - 1) / e->n_halves)) + 31) & ~31;
         e->n_halves = (int)((E + per - 1) / per);
@@ -571,6 +573,9 @@ extern "C" int tc_load_weights(tc_engine *e, const tc_net_desc *desc, const floa
         TC_TRY(e->net32x[h - 1].upload(e->folded, std::max(e->hts[h].E, 1)));
         e->net16x[h - 1].upload(e->folded, std::max(e->hts[h].E, 1), true);
     }
+    // the uploads above are blocking cudaMemcpy / cudaMemset calls on the legacy stream, while every engine stream is
+    // non-blocking: make sure the last DMA and zero-fill have landed before a search can be enqueued
+    TC_CUDA(cudaDeviceSynchronize());
     e->have_weights = true;
     return TC_OK;
 }
@@ -807,4 +812,19 @@ extern "C" int tc_selfplay_drain_dev(tc_engine *e, int max, tc_example *out_dev,
 {
     TC_TRY(check_engine(e));
     return drain_common(e, max, out_dev, false, count_out);
+}
+
+extern "C" int tc_examples_from_records_dev(tc_engine *e, int n_out, const tc_example *records_dev, int n_records,
+                                            const int32_t *index_dev, float *obs_dev, float *pi_dev, float *z_dev)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(n_out >= 0 && n_records >= 0, TC_EINVAL, "tc_examples_from_records_dev: negative count");
+    if (n_out == 0) return TC_OK;
+    TC_CHECK(records_dev && obs_dev && pi_dev && z_dev, TC_EINVAL, "tc_examples_from_records_dev: null buffer");
+    TC_CHECK(index_dev || n_out <= 8 * (long long)n_records, TC_EINVAL,
+             "tc_examples_from_records_dev: %d outputs from %d records without an index list", n_out, n_records);
+    launch_examples_from_records(n_out, records_dev, n_records, index_dev, obs_dev, pi_dev, z_dev, e->stream);
+    e->launches += 1;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
 }

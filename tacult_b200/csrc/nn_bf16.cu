@@ -540,12 +540,6 @@ struct NetBF16Impl {
     DevBuf<__nv_bfloat16> conv_w_all;      // [n_conv][9][C][C]
     DevBuf<__nv_bfloat16> bias_tiles;      // [1 + n_conv][C][16]: bias as a K-major UMMA operand (hi, lo, 0...)
     CUtensorMap map_conv_w_all, map_bias_tiles;
-    bool fused_p16 = false;                // pitch-16 layout + stacked dx taps (nn_fused_p16.cu); shares the dx weight packing
-    int p16_G = 0, p16_T = 0;
-    bool fused_dx = false;                 // 3C-column formulation (nn_fused_dx.cu)
-    int dx_G = 0, dx_T = 0;
-    DevBuf<__nv_bfloat16> dx_stem_w, dx_conv_w, dx_bias;
-    CUtensorMap map_dx_stem, map_dx_conv, map_dx_bias;
     std::vector<CUtensorMap> map_conv_w;
     int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
     bool fc1_split_k = true;               // K split over a CTA pair (nn_fc1.cu); TACULT_FC1_SPLITK=0 disables
@@ -719,32 +713,6 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
             TC_TRY(upload(m.bias_tiles, btiles));
             TC_TRY(make_map(&m.map_bias_tiles, m.bias_tiles.p, (uint64_t)(1 + L) * C, 16, (uint32_t)C, 16));
             TC_TRY(make_map(&m.map_conv_w_all, m.conv_w_all.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)C, (uint32_t)C));
-            const char *dz = getenv("TACULT_FUSED_DX");
-            int dG = 0, dT = 0;
-            // opt-in: measured slower than k_trunk_fused on B200 (its row-combining epilogue is shuffle-bound), see DESIGN.md
-            m.fused_dx = dz && atoi(dz) != 0 && fused_dx_plan(C, dG, dT);
-            const char *pz = getenv("TACULT_FUSED_P16");
-            int pG = 0, pT = 0;
-            // opt-in as well: exact, but measured slower (124 vs 92 us for 4096 positions) - see nn_fused_p16.cu
-            m.fused_p16 = !m.fused_dx && pz && atoi(pz) != 0 && fused_p16_plan(C, pG, pT);
-            if (m.fused_p16) {
-                m.p16_G = pG;
-                m.p16_T = pT;
-            }
-            if (m.fused_dx || m.fused_p16) {
-                m.dx_G = dG;
-                m.dx_T = dT;
-                std::vector<__nv_bfloat16> sw, cw, bt;
-                fused_dx_pack_stem(f.stem_w, C, I, sw);
-                fused_dx_pack_weights(f.conv_w, C, cw);
-                fused_dx_bias_tiles(ball, C, bt);
-                TC_TRY(upload(m.dx_stem_w, sw));
-                TC_TRY(upload(m.dx_conv_w, cw));
-                TC_TRY(upload(m.dx_bias, bt));
-                TC_TRY(make_map(&m.map_dx_stem, m.dx_stem_w.p, (uint64_t)9 * C, 16, (uint32_t)(3 * C), 16));
-                TC_TRY(make_map(&m.map_dx_conv, m.dx_conv_w.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)(3 * C), (uint32_t)C));
-                TC_TRY(make_map(&m.map_dx_bias, m.dx_bias.p, (uint64_t)(1 + L) * 3 * C, 16, (uint32_t)(3 * C), 16));
-            }
         }
     }
     const size_t budget = 200 * 1024;
@@ -809,15 +777,8 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
     const int total = 2 * m.d.num_residual_blocks;
     if (m.fused && to_flat && n_convs >= total) {
         prof->begin(TC_K_NN_CONV, st);
-        if (m.fused_p16)
-            launch_trunk_p16(C, m.map_dx_stem, m.map_dx_conv, m.map_dx_bias, m.p16_G, m.p16_T, total, I, batch, count_dev, states,
-                             obs, m.flat.p, m.sm_count, st);
-        else if (m.fused_dx)
-            launch_trunk_dx(C, m.map_dx_stem, m.map_dx_conv, m.map_dx_bias, m.dx_G, m.dx_T, total, I, batch, count_dev, states,
-                            obs, m.flat.p, m.sm_count, st);
-        else
-            launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.map_bias_tiles, m.fused_G, m.fused_T, total, I, batch,
-                               count_dev, states, obs, m.flat.p, m.sm_count, st);
+        launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.map_bias_tiles, m.fused_G, m.fused_T, total, I, batch,
+                           count_dev, states, obs, m.flat.p, m.sm_count, st);
         prof->end(st);
         ++launches;
         return -1;

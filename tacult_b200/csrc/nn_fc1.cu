@@ -189,10 +189,13 @@ int launch_fc1_splitk(const CUtensorMap &a, const CUtensorMap &b, int batch, con
     P.bias = bias;
     P.out = out;
     const size_t smem = fc1_splitk_smem(stages);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in is per device: one flag per ordinal (several engines on different devices may share the process)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         TC_CUDA(cudaFuncSetAttribute(fc1::k_fc1_splitk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * ((batch + 127) / 128) * P.n_blocks);

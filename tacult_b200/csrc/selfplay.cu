@@ -217,6 +217,69 @@ __global__ void k_reset_marked(TreeStore ts, SelfPlayStore sp)
     }
 }
 
+// Training examples from trajectory records (coach.py:136-149): one warp per output example.
+// Image k = 2 i + flip of getSymmetries (utac_game.py:188-190): np.rot90(x, i) then, if flip, np.fliplr.
+// rot90 once maps out[r][c] = in[c][8 - r]; the source cell of output cell (r, c) is found by undoing flip, then i turns.
+__global__ void __launch_bounds__(256) k_examples_from_records(int n_out, const tc_example *__restrict__ records,
+                                                               int n_records, const int32_t *__restrict__ index,
+                                                               float *__restrict__ obs, float *__restrict__ pi,
+                                                               float *__restrict__ z)
+{
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_out) return;
+    const int ex = index ? index[row] : row;
+    const int rec_i = ex >> 3, image = ex & 7;
+    float *o = obs + 324 * (size_t)row, *po = pi + 81 * (size_t)row;
+    if (rec_i < 0 || rec_i >= n_records) {          // out-of-range index: a zero example, never a wild read
+        for (int a = lane; a < 324; a += 32) o[a] = 0.f;
+        for (int a = lane; a < 81; a += 32) po[a] = 0.f;
+        if (lane == 0) z[row] = 0.f;
+        return;
+    }
+    const tc_example *rec = records + rec_i;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = rec->state[k];
+    Pos p = unpack(w);
+    uint32_t lw[3];
+    legal_words(p, summarize(p), lw);
+    const int turns = image >> 1;
+    const bool flip = (image & 1) != 0;
+    uint32_t total = 0;
+    for (int a = lane; a < 81; a += 32) total += rec->counts[a];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+    const bool proportional = rec->tau_one != 0 && total > 0;
+    const int played = rec->action;
+    for (int a = lane; a < 81; a += 32) {
+        int r = a / 9, c = a - 9 * r;
+        if (flip) c = 8 - c;
+        for (int t = 0; t < turns; ++t) {           // out[r][c] = in[c][8 - r]
+            const int nr = c, nc = 8 - r;
+            r = nr;
+            c = nc;
+        }
+        const int src = 9 * r + c;
+        const bool mine = action_bit(p.mine, src), occ = action_bit(p.occ, src);
+        o[a] = mine ? 1.f : 0.f;
+        o[81 + a] = (occ && !mine) ? 1.f : 0.f;
+        o[162 + a] = action_bit(lw, src) ? 1.f : 0.f;
+        o[243 + a] = 1.f;
+        // float(float64(count) / float64(total)): the reference divides in float64 (mcts.py:211-213) and converts to
+        // float32 once (coach.py:138)
+        po[a] = proportional ? (float)((double)rec->counts[src] / (double)total) : (src == played ? 1.f : 0.f);
+    }
+    if (lane == 0) z[row] = (float)((double)rec->z_sign * (rec->finished == 2 ? 1e-4 : 1.0));
+}
+
+void launch_examples_from_records(int n_out, const tc_example *records, int n_records, const int32_t *index, float *obs,
+                                  float *pi, float *z, cudaStream_t st)
+{
+    if (n_out <= 0) return;
+    k_examples_from_records<<<ceil_div(n_out, 8), 256, 0, st>>>(n_out, records, n_records, index, obs, pi, z);
+}
+
 void launch_selfplay_init(const SelfPlayStore &sp, cudaStream_t st)
 {
     k_selfplay_init<<<ceil_div(sp.E, 256), 256, 0, st>>>(sp);

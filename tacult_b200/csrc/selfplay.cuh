@@ -31,6 +31,8 @@ struct SelfPlayStore {
 void launch_selfplay_init(const SelfPlayStore &sp, cudaStream_t st);
 void launch_selfplay_roots(const SelfPlayStore &sp, cudaStream_t st);
 void launch_selfplay_move(const TreeStore &ts, const SelfPlayStore &sp, tc_selfplay_config cfg, cudaStream_t st);
+void launch_examples_from_records(int n_out, const tc_example *records, int n_records, const int32_t *index, float *obs,
+                                  float *pi, float *z, cudaStream_t st);
 void launch_reset_marked(const TreeStore &ts, const SelfPlayStore &sp, cudaStream_t st);
 
 }  // namespace tc

@@ -21,7 +21,13 @@ def pack_fields(board, occ, last_square):
 
 
 def pack_gamestates(boards):
-    """list of utac_gym GameState (canonical frame) -> (packed u32[n,8], active u8[n]); None -> inactive."""
+    """list of GameState (canonical frame) -> (packed u32[n,8], active u8[n]); None -> inactive.
+    tacult_b200.GameState objects go through one C call (tc_gs_pack); objects of another rules package (the real
+    utac_gym) are read field by field through their `_get_gs()`."""
+    from .gamestate import pack_states
+    fast = pack_states(boards)
+    if fast is not None:
+        return fast
     n = len(boards)
     b = np.zeros((n, 9), dtype=np.uint32)
     o = np.zeros((n, 9), dtype=np.uint32)

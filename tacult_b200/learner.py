@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 from .network import TrunkNet
+from .weights import _strip
 
 
 class Learner:
@@ -91,6 +92,13 @@ class Learner:
                     cursor = 0
                 idx = order[cursor:cursor + batch_size]
                 cursor += batch_size
+                if len(idx) < 2 * self.world and n >= 2 * self.world:
+                    # ragged tail too short to give every rank the two rows train-mode BatchNorm needs (a rank that
+                    # raised there would leave the others hanging in the all-reduce): top it up from the next permutation
+                    short = len(idx)
+                    order = torch.randperm(n, generator=gen) if shuffle else torch.arange(n)
+                    cursor = min(n, batch_size - short)
+                    idx = torch.cat([idx, order[:cursor]])
                 mine = idx[self.rank::self.world]
                 a, b = self.training_step(obs[mine], pi[mine], z[mine], global_batch=len(idx))
                 tot_pi += a
@@ -122,7 +130,7 @@ class Learner:
         if not os.path.exists(path):
             raise FileNotFoundError(f"No model found at {path}")                 # nn_wrapper.py:169-171
         ckpt = torch.load(path, map_location=self.device, weights_only=False)
-        self.net.load_state_dict(ckpt["state_dict"])
+        self.net.load_state_dict(_strip(ckpt["state_dict"]))      # torch.compile'd reference nets prefix "_orig_mod."
         if "optimizer" in ckpt:
             self.optimizer.load_state_dict(ckpt["optimizer"])
 
@@ -131,7 +139,7 @@ def load_reference_checkpoint(path, map_location="cpu"):
     """A reference `.pt` (nn_wrapper.py:160-163) -> (state_dict of numpy arrays, optimizer state or None).
     Feed the state_dict to `Engine.load_weights` or `TrunkNet.from_state_dict`."""
     ckpt = torch.load(path, map_location=map_location, weights_only=False)
-    sd = {k: v.detach().cpu().numpy() for k, v in ckpt["state_dict"].items()}
+    sd = {k: v.detach().cpu().numpy() for k, v in _strip(ckpt["state_dict"]).items()}
     return sd, ckpt.get("optimizer")
 
 

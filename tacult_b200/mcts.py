@@ -7,6 +7,7 @@ expansion, backup, move generation and the network forward all run on the GPU th
 this class only converts between `GameState` objects and packed positions.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -19,6 +20,32 @@ def _opt(args, key, default):
         return args[key]
     except (KeyError, TypeError):
         return getattr(args, key, default) if not isinstance(args, dict) else default
+
+
+_rules_checked = False
+
+
+def check_foreign_rules_engine():
+    """The observation planes and the UTTT rule choices of this engine are NOT pinned by the
+    reference: its rules live in the external `utac_gym`.  When a real `utac_gym` is importable, compare it with the
+    engine's rules on random playouts once per process and fail loudly on a difference (a reference-trained checkpoint
+    would otherwise see other inputs than it was trained on).  TACULT_SKIP_RULES_SELFCHECK=1 skips the check."""
+    global _rules_checked
+    if _rules_checked or os.environ.get("TACULT_SKIP_RULES_SELFCHECK") == "1":
+        return
+    _rules_checked = True
+    try:
+        import utac_gym
+        from utac_gym.core import GameState as Foreign
+    except ImportError:
+        return
+    from .gamestate import GameState, self_check_against
+    if Foreign is GameState or getattr(utac_gym, "_tacult_b200_shim", False):
+        return
+    try:
+        self_check_against(Foreign, games=16)
+    except AssertionError as exc:
+        raise RuntimeError(f"tacult_b200's rules / observation planes differ from the installed utac_gym: {exc}") from exc
 
 
 class VectorizedMCTS:
@@ -44,6 +71,7 @@ class VectorizedMCTS:
         self.engine = Engine(num_envs, cap_nodes, cap_edges, device=device,
                              eval_log_capacity=int(_opt(args, "tc_eval_log_capacity", 0)))
         self._bind_evaluator(nnet, args)
+        check_foreign_rules_engine()
 
     def _bind_evaluator(self, nnet, args):
         hp = getattr(nnet, "tc_hash_params", None)
@@ -76,16 +104,40 @@ class VectorizedMCTS:
 
     def getActionProbs(self, canonicalBoards, temps):     # mcts.py:175-214
         counts_all = self.rootCounts(canonicalBoards)
-        n_env, n_act = counts_all.shape
-        probs = np.zeros((n_env, n_act))
-        for i in range(n_env):
-            counts = counts_all[i]
-            temp = temps[i]
-            if temp == 0:
-                best = np.array(np.argwhere(counts == np.max(counts))).ravel()
-                probs[i][np.random.choice(best)] = 1          # same global-RNG draw as the reference (mcts.py:207-208)
-            else:
-                powered = counts ** (1. / temp)
-                with np.errstate(invalid="ignore", divide="ignore"):
-                    probs[i] = powered / float(np.sum(powered))   # finished envs give NaN rows, as in the reference
-        return probs
+        return action_probs_from_counts(counts_all, temps)
+
+
+def action_probs_from_counts(counts_all, temps):
+    """The tail of getActionProbs (mcts.py:191-214) for all envs at once, with the reference's results and the
+    reference's draws from the global `np.random` stream:
+      temp == 0: one-hot on an arg-max of the counts, ties broken by `np.random.choice(bestAs)` (mcts.py:206-209).
+                 `choice` over k candidates is one `randint(0, k)`, which draws nothing when k == 1 — so only rows
+                 with a tie touch the generator, in env order, exactly as the per-env loop does;
+      temp == 1: counts / sum — integers, exact in float64 whatever the summation order (mcts.py:211-213);
+      any other temp: the reference's expression row by row."""
+    counts_all = np.asarray(counts_all)
+    n_env, n_act = counts_all.shape
+    temps = np.asarray(temps)
+    probs = np.zeros((n_env, n_act))
+    zero = temps == 0
+    one = temps == 1
+    if one.any():
+        c = counts_all[one].astype(np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            probs[one] = c / c.sum(axis=1, keepdims=True)          # finished envs give NaN rows, as in the reference
+    if zero.any():
+        rows = np.flatnonzero(zero)
+        c = counts_all[rows]
+        top = c.max(axis=1)
+        is_top = c == top[:, None]
+        ties = is_top.sum(axis=1)
+        pick = is_top.argmax(axis=1)
+        for k in np.flatnonzero(ties > 1):                           # ascending env order: same draw sequence
+            best = np.flatnonzero(is_top[k])
+            pick[k] = best[np.random.randint(0, len(best))]       # what np.random.choice(best) does inside
+        probs[rows, pick] = 1
+    for i in np.flatnonzero(~(zero | one)):
+        powered = counts_all[i] ** (1. / temps[i])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            probs[i] = powered / float(np.sum(powered))
+    return probs

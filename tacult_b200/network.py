@@ -55,6 +55,8 @@ class TrunkNet(nn.Module):
     @classmethod
     def from_state_dict(cls, state_dict, dropout=0.3):
         """Architecture read off the tensor shapes (as weights.state_dict_to_blob does)."""
+        from .weights import _strip
+        state_dict = _strip(state_dict)          # torch.compile'd reference checkpoints prefix "_orig_mod."
         channels = int(state_dict["conv_in.weight"].shape[0])
         in_planes = int(state_dict["conv_in.weight"].shape[1])
         blocks = 1 + max(int(k.split(".")[1]) for k in state_dict if k.startswith("resnet."))

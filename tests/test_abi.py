@@ -27,7 +27,7 @@ def test_binding_covers_header():
     from tacult_b200 import _lib
     assert sorted(_lib.SYMBOLS) == declared_symbols()
     lib = _lib.load()
-    assert lib.tc_abi_version() == 1
+    assert lib.tc_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_is_sm100a(built_library):
@@ -41,6 +41,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Config) == 40
     assert ctypes.sizeof(_lib.PlayoutResult) == 48
     assert ctypes.sizeof(_lib.SelfPlayConfig) == 32
+    assert ctypes.sizeof(_lib.GameStateStruct) == _lib.GAMESTATE_DTYPE.itemsize == 44
 
 
 def test_fails_loudly_without_gpu():

@@ -120,23 +120,3 @@ def test_search_with_bf16_evaluator():
     assert (counts.sum(1) == 63).all() and (counts == counts[0]).all()
     st = eng.stats()
     assert st["nn_leaves"] + st["terminal_leaves"] == 512 * 64
-
-
-@pytest.mark.parametrize("switch", ["TACULT_FUSED_DX", "TACULT_FUSED_P16"])
-@pytest.mark.parametrize("arch", [(32, 3, 256), (16, 4, 256), (64, 2, 128)])
-def test_opt_in_trunk_formulations_match_fp32_reference(arch, switch, monkeypatch):
-    """The two stacked-dx formulations of the fused trunk (nn_fused_dx.cu, nn_fused_p16.cu) are opt-in experiments;
-    they must meet the same 2e-2 bar, for batch sizes that give every group size.  (64 channels: p16 falls back.)"""
-    monkeypatch.setenv(switch, "1")          # read when the weights are uploaded
-    sd = torch_default_state_dict(7, *arch)
-    eng = tb.Engine(2048, 2)
-    eng.load_weights(sd)
-    rng = np.random.RandomState(3)
-    x = (rng.random_sample((2048, 4, 9, 9)) < 0.3).astype(np.float32)
-    pi, v, logits = eng.forward(x, BF16, want_logits=True)
-    rpi, rv, rlogits = resnet_oracle.forward(sd, x, return_logits=True)
-    assert np.abs(pi - rpi.numpy()).max() < TOL_BF16 and np.abs(v - rv.numpy().ravel()).max() < TOL_BF16
-    assert np.abs(logits - rlogits.numpy()).max() < TOL_BF16
-    for b in (1, 150, 1333, 1924):
-        p1, v1 = eng.forward(x[:b], BF16)
-        assert np.array_equal(p1, pi[:b]) and np.array_equal(v1, v[:b])
