@@ -7,9 +7,12 @@
 A "step" is one lock-step ply of every tree: `sims` simulations per live tree (select -> leaf evaluation
 -> expand/backup), move choice from the visit counts, root advance.  Workload at N=1: BASELINE.json
 configs[2] — 4096 trees x 200 sims/move, trainer-default ResNet (32 ch x 3 blocks, emb 256), random-init
-weights, synthetic self-play.  N>1: every rank runs its own 4096 trees (weak scaling, no data-path
-collective; finished trajectories are all-gathered outside the timed region).
-Prints ONE JSON line on rank 0.
+weights, synthetic self-play.  N>1: every rank runs its own 4096 trees (weak scaling, no collective on the search
+path); the `c4` leg then plays BASELINE.json configs[3] — 4096 trees x 800 sims per rank, every game to completion —
+and times the iteration's one exchange step (records drained on the device, NCCL all-gather) with it.
+Extra keys next to the contract's: `c3_full_iteration` (the reference's iteration shape: no auto-reset, finished
+envs idle), `e2e_dropin` (the Python drop-in `VectorizedMCTS.getActionProbs(list[GameState])`), `deep_net`
+(configs[4] trunk roofline), `c4` (N>1).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -41,9 +44,12 @@ def parse():
     ap.add_argument("--stagger-plies", type=int, default=150)
     ap.add_argument("--profile-plies", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--ref-envs", type=int, default=16, help="trees in the host-CPU sample (reference arm)")
+    ap.add_argument("--ref-envs", type=int, default=64,
+                    help="trees in the host-CPU sample of the reference arm (64 = the reference's own C1 width)")
+    ap.add_argument("--c4-sims", type=int, default=800)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="no c3_full_iteration / e2e_dropin / deep_net / c4 legs")
     return ap.parse_args()
 
 
@@ -98,12 +104,65 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# host-CPU arm: the reference algorithm (oracle port; /root/reference is Python and cannot travel)
+# host-CPU arm: the reference's own Python when it is available (/root/reference here, the byte-for-byte staged copy
+# under oracle/_ref on the GPU box), else the oracle port
 # ------------------------------------------------------------------------------------------------
-def cpu_selfplay_rate(envs, sims, seconds=None, plies=None, warmup_plies=0, seed=0):
-    """Times the reference's CPU path — lock-step VectorizedMCTS + rules engine + torch-CPU ResNet forward —
-    as restated in oracle/ (mcts_oracle.py, game_oracle.py, resnet_oracle.py), on `envs` trees x `sims` sims.
-    Returns (sims_per_second, plies_timed, seconds_timed, per_ply_ms list)."""
+def live_reference_selfplay(envs, sims, seconds=None, plies=None, warmup_plies=0, seed=0):
+    """The UNMODIFIED reference: `Coach.prepExecuteEpisode/executeEpisode` (base/coach.py:87-157) driving its
+    `VectorizedMCTS` (base/mcts.py:147-358) over `UtacGame` and `UtacNN` (`_UtacNNet` eager on torch CPU, all host
+    threads); the external rules engine `utac_gym` is served by oracle/utac_gym.  Returns None when the reference
+    modules are not available."""
+    import contextlib
+    import io
+    import logging
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    if not ref_loader.reference_available() and not os.path.isfile(
+            os.path.join(ROOT, "oracle", "_ref", "src", "tacult", "base", "mcts.py")):
+        return None
+    try:
+        ref = ref_loader.load_reference()
+    except Exception as exc:                      # a dependency of the reference modules is missing on this box
+        sys.stderr.write(f"[bench] live reference not loadable ({exc!r}); using the oracle port\n")
+        return None
+    logging.disable(logging.ERROR)
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    np.random.seed(seed)
+    args = ref.utils.dotdict(numIters=1, numEnvs=envs, minNumEps=envs, numMCTSSims=sims, cpuct=CPUCT,
+                             tempThreshold=TEMP_THRESHOLD, steps_per_epoch=10, epochs=10, batch_size=4096, lr=3e-3,
+                             num_warm_restarts=3, onnx_export=True, cuda=False,
+                             model_args=dict(dropout=0.2, cuda=False, **NET))
+    coach = ref.coach.Coach.__new__(ref.coach.Coach)          # __init__ only adds checkpoint folders and an arena
+    coach.game, coach.args, coach.pnet = ref.utac_game.UtacGame(), args, ref.utac_nn.UtacNN(args)
+    mcts = ref.mcts.VectorizedMCTS(coach.game, coach.pnet, args)
+    coach.prepExecuteEpisode()
+
+    def one_ply():
+        live = int((~coach._autoresetEnvs).sum())
+        with contextlib.redirect_stdout(io.StringIO()):
+            coach.executeEpisode(mcts)
+        return live
+
+    for _ in range(warmup_plies):
+        one_ply()
+    t0 = time.perf_counter()
+    done, n, per_ply = 0, 0, []
+    while True:
+        t1 = time.perf_counter()
+        live = one_ply()
+        done += live * sims
+        per_ply.append((time.perf_counter() - t1) * 1e3)
+        n += 1
+        if live == 0 or (plies is not None and n >= plies) or (seconds is not None and time.perf_counter() - t0 >= seconds):
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, n, dt, per_ply, os.path.relpath(ref.root, ROOT) if ref.root.startswith(ROOT) else ref.root
+
+
+def port_selfplay_rate(envs, sims, seconds=None, plies=None, warmup_plies=0, seed=0):
+    """Fallback: the reference's CPU path as restated in oracle/ (mcts_oracle.py, game_oracle.py, resnet_oracle.py)."""
     import logging
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -123,38 +182,43 @@ def cpu_selfplay_rate(envs, sims, seconds=None, plies=None, warmup_plies=0, seed
     boards = [game.getInitBoard() for _ in range(envs)]
     players = np.ones(envs, dtype=int)
     step_no = np.zeros(envs, dtype=int)
+    over = np.zeros(envs, dtype=bool)
 
     def one_ply():
-        nonlocal mcts
-        live = 0
+        live = int((~over).sum())
         step_no[:] += 1
         canon = [game.getCanonicalForm(boards[i], players[i]) for i in range(envs)]
         probs = mcts.getActionProbs(canon, temps=(step_no < TEMP_THRESHOLD))
         for i in range(envs):
-            if game.getGameEnded(boards[i], players[i]) != 0:      # restart finished games (keeps the sample busy)
-                boards[i], players[i], step_no[i] = game.getInitBoard(), 1, 0
-                mcts.reset(i)
+            if over[i]:
                 continue
-            live += 1
             a = np.random.choice(81, p=probs[i])
             boards[i], players[i] = game.getNextState(boards[i], int(players[i]), a)
+            over[i] = game.getGameEnded(boards[i], players[i]) != 0
         return live
 
     for _ in range(warmup_plies):
         one_ply()
     t0 = time.perf_counter()
-    done_sims, n, per_ply = 0, 0, []
+    done, n, per_ply = 0, 0, []
     while True:
         t1 = time.perf_counter()
-        done_sims += one_ply() * sims
+        live = one_ply()
+        done += live * sims
         per_ply.append((time.perf_counter() - t1) * 1e3)
         n += 1
-        if plies is not None and n >= plies:
-            break
-        if seconds is not None and time.perf_counter() - t0 >= seconds:
+        if live == 0 or (plies is not None and n >= plies) or (seconds is not None and time.perf_counter() - t0 >= seconds):
             break
     dt = time.perf_counter() - t0
-    return done_sims / dt, n, dt, per_ply
+    return done / dt, n, dt, per_ply, "oracle/"
+
+
+def host_selfplay_rate(envs, sims, **kw):
+    """(kind, sims/s, plies, seconds, per-ply ms, source): the live reference when it can be loaded, else the port."""
+    out = live_reference_selfplay(envs, sims, **kw)
+    if out is not None:
+        return ("reference",) + out
+    return ("port",) + port_selfplay_rate(envs, sims, **kw)
 
 
 def run_reference(a):
@@ -162,28 +226,32 @@ def run_reference(a):
     if rank != 0:
         return
     import torch
-    rate, n, dt, per_ply = cpu_selfplay_rate(a.ref_envs, a.sims, plies=a.steps, warmup_plies=a.warmup)
+    kind, rate, n, dt, per_ply, source = host_selfplay_rate(a.ref_envs, a.sims, plies=a.steps, warmup_plies=a.warmup)
     cores = torch.get_num_threads()
-    sample = (f"{a.ref_envs} of the {a.envs} trees x {a.sims} sims/move, {a.steps} plies after {a.warmup} warm-up, "
-              f"oracle port of VectorizedMCTS+rules+torch-CPU ResNet")
+    what = ("the unmodified reference (Coach.executeEpisode -> VectorizedMCTS -> UtacGame -> _UtacNNet, torch CPU eager) "
+            f"from {source}, rules engine utac_gym served by oracle/utac_gym") if kind == "reference" else \
+        "oracle port of VectorizedMCTS + rules + torch-CPU ResNet"
+    sample = (f"{a.ref_envs} of the {a.envs} trees x {a.sims} sims/move from the initial position, {n} plies after "
+              f"{a.warmup} warm-up plies in {dt:.1f} s; {what}; the Python search loop is single-threaded, the network "
+              f"forward uses {cores} threads")
     line = {
         "impl": "reference", "metric": "mcts_sims_per_sec_selfplay", "value": rate, "unit": "sims/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(per_ply)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, "cpu"),
-        "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample,
-                         "host_cpus": os.cpu_count()},
+        "config": workload_config(a),
+        "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": kind, "sample": sample,
+                         "sample_trees": a.ref_envs, "host_cpus": os.cpu_count()},
         "e2e": {"value": rate, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(a, evaluator):
+def workload_config(a):
+    """Identical in both arms (the reference arm times a bounded sample of it, stated in its cpu_baseline.sample)."""
     return {"workload": f"self-play {a.envs} trees x {a.sims} sims/move per GPU, trainer-default ResNet "
                         f"(32ch x 3 blocks, emb 256), random init",
             "trees_per_gpu": a.envs, "sims_per_move": a.sims, "cpuct": CPUCT, "temp_threshold": TEMP_THRESHOLD,
-            "evaluator": evaluator, "tree_arithmetic": "f64",
-            "stagger": f"{a.stagger_plies} plies @2 sims with auto-reset before warm-up",
+            "tree_arithmetic": "f64",
             "l2": "working set (tree store + activations) exceeds the 126 MB L2; no explicit flush",
             "parallelism": f"trees sharded by index, {a.gpus} x {a.envs}"}
 
@@ -281,27 +349,37 @@ def run_b200(a):
     if not a.skip_e2e:
         e2e = run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world)
 
-    # ---- N>1: the one exchange step — finished trajectories all-gathered over NCCL (outside the timed region)
+    extras = {}
+    if not a.skip_extras:
+        # ---- the reference's iteration shape (coach.py:160-193): E games from the initial position to completion, no
+        #      auto-reset, finished envs idle (coach.py:114-122,133-134), so the last plies run nearly empty batches ----
+        extras["c3_full_iteration"] = full_iteration(eng, torch, stream, sims, seed, barrier, reduce_scalar, dist, world)
+        # ---- the Python drop-in under the reference's own calling convention ----
+        if rank == 0:
+            extras["e2e_dropin"] = run_dropin(a, eng, tb, torch, evaluator)
+        barrier()
+    eng.close()
+
+    # ---- BASELINE.json configs[4]: the deep 256ch x 20 trunk, where the conv GEMMs are tensor-bound -------------
+    if not a.skip_extras:
+        extras["deep_net"] = deep_net_leg(tb, torch, stream, local, reduce_scalar, dist, world)
+
+    # ---- N>1, BASELINE.json configs[3]: 4096 trees x 800 sims per rank, every game to completion, then the iteration's
+    #      one exchange step — records drained on the device and all-gathered over NCCL — inside the measured span -----
     gathered = None
-    if world > 1:
-        from tacult_b200.distributed import all_gather_records
-        eng.selfplay_configure(sims, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True)
-        eng.selfplay_drain()
-        eng.selfplay_step(2)
-        eng.selfplay_sync()
-        local_recs = eng.selfplay_drain()
-        t0 = time.perf_counter()
-        allrec = all_gather_records(local_recs, device=torch.device("cuda", local_dev))
-        torch.cuda.synchronize()
-        gathered = {"records_local": int(len(local_recs)), "records_all_ranks": int(len(allrec)),
-                    "ms": 1e3 * (time.perf_counter() - t0), "bytes_per_record": 216}
+    if world > 1 and not a.skip_extras:
+        extras["c4"], gathered = c4_leg(a, tb, torch, stream, local, rank, world, evaluator, barrier, reduce_scalar, dist)
 
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu_baseline:
-        rate, n, dt, _ = cpu_selfplay_rate(64, 25, seconds=a.cpu_seconds)
-        cpu = {"value": rate, "unit": "sims/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"BASELINE config C1 shape: 64 trees x 25 sims/move, {n} plies in {dt:.1f} s, oracle port of "
-                         f"VectorizedMCTS+rules+torch-CPU ResNet (python search loop is single-threaded)",
+        kind, rate, n, dt, _, source = host_selfplay_rate(64, 25, seconds=a.cpu_seconds)
+        cpu = {"value": rate, "unit": "sims/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"BASELINE config C1 shape: 64 trees x 25 sims/move from the initial position, {n} plies in "
+                         f"{dt:.1f} s, " + ("the unmodified reference Python (Coach.executeEpisode -> VectorizedMCTS -> "
+                                            f"UtacGame -> _UtacNNet on torch CPU) from {source}, utac_gym served by "
+                                            "oracle/utac_gym" if kind == "reference" else
+                                            "oracle port of VectorizedMCTS+rules+torch-CPU ResNet")
+                         + " (python search loop is single-threaded)",
                "host_cpus": os.cpu_count()}
 
     if rank == 0:
@@ -309,16 +387,212 @@ def run_b200(a):
             "metric": "mcts_sims_per_sec_selfplay", "value": value, "unit": "sims/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": evaluator, "data": "synthetic",
-            "config": workload_config(a, evaluator),
+            "config": workload_config(a),
+            "measured_region": f"steady state: {a.stagger_plies} plies @2 sims with auto-reset spread the envs over all "
+                               f"game phases, then {a.warmup} warm-up + {a.steps} timed plies with auto-reset; the "
+                               f"reference's own iteration shape is under c3_full_iteration",
             "leaf_evals_per_sec": leaves * world / (ms * 1e-3),
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roof, "kernels": kernels,
+            "kernels_note": "per-kernel times come from a separate pass that brackets every launch with CUDA events; the "
+                            "events serialise the programmatic dependent launches, so that pass runs ~10 % slower per ply "
+                            "than the headline (shares, not absolutes)",
             "e2e": e2e, "cpu_baseline": cpu, "trajectory_all_gather": gathered,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def full_iteration(eng, torch, stream, sims, seed, barrier, reduce_scalar, dist, world):
+    """E games to completion, Σ(live envs x sims) / device time between the first and the last ply."""
+    E = eng.num_envs
+    eng.selfplay_begin(sims, CPUCT, TEMP_THRESHOLD, seed=seed + 77, auto_reset=False)
+    eng.selfplay_sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    k0 = eng.stats()
+    ev0.record(stream)
+    plies = 0
+    while plies < 81:
+        eng.selfplay_step(1)
+        plies += 1
+        if plies >= 17 and eng.selfplay_stats()["games_finished"] >= E:      # no game ends before ply 17
+            break
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    eng.selfplay_sync()
+    st, k1 = eng.selfplay_stats(), eng.stats()
+    ms = reduce_scalar(ev0.elapsed_time(ev1), dist.ReduceOp.MAX if world > 1 else None)
+    sims_done = reduce_scalar(float(st["sims"]), dist.ReduceOp.SUM if world > 1 else None)
+    records = int(st["examples"])
+    eng.selfplay_drain()
+    return {"value": sims_done / (ms * 1e-3), "unit": "sims/s", "seconds": ms * 1e-3, "plies": plies,
+            "games": int(st["games_finished"]) * world, "env_plies": int(st["plies"]),
+            "mean_live_fraction": st["plies"] / float(plies * E), "records": records,
+            "leaf_evals_per_sec": (k1["nn_leaves"] - k0["nn_leaves"]) * world / (ms * 1e-3),
+            "shape": f"{E} games per GPU from the initial position to completion, {sims} sims/move, no auto-reset "
+                     "(base/coach.py:160-193)"}
+
+
+def run_dropin(a, eng, tb, torch, evaluator):
+    """`tacult_b200.VectorizedMCTS.getActionProbs(list[GameState], temps)` — the call `Coach.executeEpisode` makes
+    (coach.py:131) — on 4096 GameState objects x 200 sims: the timed span is the drop-in's own call (host packing of
+    the objects, H2D, search, D2H, host tail); moving the boards between calls is the caller's code and is not timed."""
+    from tacult_b200.gamestate import GameState
+    from tacult_b200.weights import random_state_dict
+    E, sims = a.envs, a.sims
+
+    class Args(dict):
+        __getattr__ = dict.__getitem__
+
+    class Net:
+        class nnet:
+            @staticmethod
+            def state_dict():
+                return random_state_dict(0, **NET)
+    args = Args(numEnvs=E, numMCTSSims=sims, cpuct=CPUCT, tc_evaluator=evaluator, tc_max_nodes_per_tree=sims * 82 + 64,
+                tc_device=torch.cuda.current_device())
+    mcts = tb.VectorizedMCTS(None, Net(), args)
+    rng = np.random.RandomState(11)
+    depth = rng.randint(0, 40, size=E)
+    states = np.zeros((E, 8), dtype=np.uint32)
+    for d in range(40):                                   # staggered mid-game positions (live ones only)
+        todo = np.flatnonzero(depth > d)
+        if todo.size == 0:
+            break
+        mask = tb.rules_legal_mask(states[todo])
+        acts = np.array([rng.choice(np.flatnonzero(m)) for m in mask], dtype=np.int8)
+        nxt, st = tb.rules_step(states[todo], acts)
+        states[todo[st == 0]] = nxt[st == 0]
+    ply_no = np.zeros(E, dtype=np.int64)
+    total_s, pack_s, n_timed = 0.0, 0.0, 0
+    np.random.seed(3)
+    for it in range(a.warmup + a.steps):
+        boards = [GameState.from_packed(s) for s in states]               # the caller's objects
+        temps = (ply_no + 1) < TEMP_THRESHOLD
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        probs = mcts.getActionProbs(boards, temps)
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        tb.pack_gamestates(boards)
+        dp = time.perf_counter() - t1
+        if it >= a.warmup:
+            total_s += dt
+            pack_s += dp
+            n_timed += 1
+        acts = np.array([np.random.choice(81, p=p) for p in probs], dtype=np.int8)       # coach.py:140
+        nxt, st = tb.rules_step(states, acts)
+        states[:] = nxt
+        ply_no += 1
+        for i in np.flatnonzero(st != 0):
+            states[i] = 0
+            ply_no[i] = 0
+            mcts.reset(int(i))
+    from tacult_b200.mcts import action_probs_from_counts
+    counts = mcts.engine.root_counts().astype(np.int64)
+    t2 = time.perf_counter()
+    action_probs_from_counts(counts, temps)
+    tail_ms = 1e3 * (time.perf_counter() - t2)
+    mcts.engine.close()
+    return {"value": E * sims * n_timed / total_s, "unit": "sims/s", "ms_per_call": 1e3 * total_s / n_timed,
+            "host_pack_ms": 1e3 * pack_s / n_timed, "host_probs_ms": tail_ms,
+            "h2d_bytes_per_step": E * 33, "d2h_bytes_per_step": E * 81 * 4,
+            "path": "VectorizedMCTS.getActionProbs(list of 4096 tacult_b200.GameState, temps): tc_gs_pack -> "
+                    "tc_set_roots_packed -> tc_search -> tc_root_counts -> vectorised counts->probs (global np.random "
+                    "draws as the reference's)"}
+
+
+def deep_net_leg(tb, torch, stream, local, reduce_scalar, dist, world):
+    """BASELINE.json configs[4] on this rank: 20 blocks x 256 channels, batch 4096 leaf evaluations resident in HBM;
+    algorithmic FLOPs / device time against the measured sustained bf16 peak."""
+    from tacult_b200.weights import flops_per_eval, random_state_dict
+    C, B, E, batch, iters = 256, 20, 256, 4096, 5
+    eng = tb.Engine(batch, 2, device=local)
+    eng.set_stream(stream.cuda_stream)
+    eng.load_weights(random_state_dict(0, C, B, E))
+    res = tb.rules_playouts(1, 0, batch, max_plies=30)
+    states = torch.from_numpy(np.array([list(r.final_state) for r in res], dtype=np.uint32).view(np.int32)).cuda()
+    pi = torch.empty((batch, 81), dtype=torch.float32, device="cuda")
+    v = torch.empty((batch,), dtype=torch.float32, device="cuda")
+
+    def run():
+        tb._lib.check(eng.lib.tc_forward_states_dev(eng.handle, tb._lib.EVAL_NET_BF16, batch, states.data_ptr(),
+                                                   pi.data_ptr(), v.data_ptr()))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = reduce_scalar(e0.elapsed_time(e1) / iters, dist.ReduceOp.MAX if world > 1 else None)
+    eng.close()
+    peaks = measured_peaks()
+    tf = flops_per_eval(C, B, E) * batch / (ms * 1e-3) / 1e12
+    return {"workload": "256ch x 20 blocks, batch 4096 per GPU, bf16, inputs resident in HBM", "ms": ms,
+            "evals_per_sec": batch * world / (ms * 1e-3), "tflops_per_gpu": tf,
+            "frac_of_sustained_bf16_peak": tf / peaks["bf16_tflops_sustained"],
+            "frac_of_burst_bf16_peak": tf / peaks["bf16_tflops"]}
+
+
+def c4_leg(a, tb, torch, stream, local, rank, world, evaluator, barrier, reduce_scalar, dist):
+    from tacult_b200.distributed import DeviceReplay, DeviceTrajectoryExchange
+    from tacult_b200.weights import random_state_dict
+    E, sims = a.envs, a.c4_sims
+    eng = tb.Engine(E, sims * 82 + 64, device=local)
+    eng.set_stream(stream.cuda_stream)
+    eng.load_weights(random_state_dict(0, **NET))
+    eng.set_evaluator(tb._lib.EVAL_NET_BF16 if evaluator == "bf16" else tb._lib.EVAL_NET_F32)
+    xchg = DeviceTrajectoryExchange(eng, torch.device("cuda", local))
+    eng.selfplay_begin(sims, CPUCT, TEMP_THRESHOLD, seed=5000 + rank, auto_reset=False)
+    eng.selfplay_sync()
+    dist.all_reduce(torch.zeros(1, device="cuda"))            # NCCL communicator up before the clock starts
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    barrier()
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    plies = 0
+    while plies < 81:
+        eng.selfplay_step(1)
+        plies += 1
+        if plies >= 17 and eng.selfplay_stats()["games_finished"] >= E:
+            break
+    ev[1].record(stream)
+    records, counts = xchg.gather()                            # drain on the device + counts + padded all-gather
+    replay = DeviceReplay(eng, records)
+    ev[2].record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    eng.selfplay_sync()
+    st = eng.selfplay_stats()
+    play_ms = reduce_scalar(ev[0].elapsed_time(ev[1]), dist.ReduceOp.MAX)
+    all_ms = reduce_scalar(ev[0].elapsed_time(ev[2]), dist.ReduceOp.MAX)
+    x_ms = reduce_scalar(ev[1].elapsed_time(ev[2]), dist.ReduceOp.MAX)
+    sims_done = reduce_scalar(float(st["sims"]), dist.ReduceOp.SUM)
+    n_total = int(sum(counts))
+    # a learner-side use of the gathered records, still on the device: one batch of examples (8 symmetries on the fly)
+    idx = torch.randint(0, max(replay.n_examples, 1), (4096,), device="cuda", dtype=torch.int32)
+    obs, pi, z = replay.examples(idx)
+    ok = bool(torch.isfinite(obs).all() and torch.isfinite(pi).all() and (pi.sum(1) - 1).abs().max() < 1e-3)
+    gathered = {"records_local": int(counts[rank]), "records_all_ranks": n_total, "ms": x_ms, "bytes_per_record": 216,
+                "effective_gbps": world * max(counts) * 216 / (x_ms * 1e-3) / 1e9 if x_ms > 0 else None,
+                "path": "tc_selfplay_drain_dev -> persistent CUDA send buffer -> all_gather_into_tensor (NCCL) -> "
+                        "device record tensor -> tc_examples_from_records_dev", "examples_ok": ok}
+    eng.close()
+    return ({"workload": f"BASELINE configs[3]: {world} x {E} trees x {sims} sims/move, every game to completion, records "
+                         "all-gathered over NCCL",
+             "value_with_exchange": sims_done / (all_ms * 1e-3), "value_without_exchange": sims_done / (play_ms * 1e-3),
+             "unit": "sims/s", "seconds_play": play_ms * 1e-3, "seconds_exchange": x_ms * 1e-3, "plies": plies,
+             "games": int(st["games_finished"]) * world, "records": n_total,
+             "exchange_share": x_ms / all_ms if all_ms else None}, gathered)
 
 
 def roofline(prof, k0, k1, a, evaluator, flops_eval):

@@ -147,6 +147,7 @@ int  tc_gs_pack(int n, const tc_gamestate *gs_host, uint32_t *states_host, uint8
 int tc_create(const tc_config *cfg, tc_engine **out);              /* VectorizedMCTS.__init__ mcts.py:152-162 */
 int tc_destroy(tc_engine *e);
 int tc_set_stream(tc_engine *e, void *cuda_stream);                /* cudaStream_t; NULL = engine-owned stream */
+int tc_sync(tc_engine *e);                                         /* waits for everything enqueued on that stream */
 int tc_reset(tc_engine *e, int env);                               /* VectorizedMCTS.reset(i) mcts.py:165-172; env<0 = all */
 int tc_set_hash_evaluator(tc_engine *e, uint64_t salt, int pi_levels, int v_levels);
 int tc_set_evaluator(tc_engine *e, int evaluator);

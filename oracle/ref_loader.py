@@ -17,9 +17,13 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("TACULT_REFERENCE_ROOT", "/root/reference")
-_SRC = os.path.join(REFERENCE_ROOT, "src", "tacult")
 _ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on the GPU box the byte-for-byte staged copy under oracle/_ref
+# (oracle/stage_reference.py, git-ignored)
+REFERENCE_ROOT = os.environ.get("TACULT_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "tacult", "base", "mcts.py")):
+    REFERENCE_ROOT = os.path.join(_ORACLE_DIR, "_ref")
+_SRC = os.path.join(REFERENCE_ROOT, "src", "tacult")
 
 
 def reference_available():
@@ -46,6 +50,7 @@ def load_reference():
         sys.modules["tacult"] = pkg
         sys.modules["tacult.base"] = base
     ns = types.SimpleNamespace()
+    ns.root = REFERENCE_ROOT
     ns.mcts = importlib.import_module("tacult.base.mcts")
     ns.utils = importlib.import_module("tacult.utils")
     ns.base_utils = importlib.import_module("tacult.base.utils")
@@ -54,4 +59,5 @@ def load_reference():
     ns.utac_game = importlib.import_module("tacult.utac_game")
     ns.arena = importlib.import_module("tacult.base.arena")
     ns.coach = importlib.import_module("tacult.base.coach")
+    ns.utac_nn = importlib.import_module("tacult.utac_nn")
     return ns

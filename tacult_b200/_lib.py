@@ -136,6 +136,7 @@ SYMBOLS = {
     "tc_create": (_i, [ctypes.POINTER(Config), ctypes.POINTER(_vp)]),
     "tc_destroy": (_i, [_vp]),
     "tc_set_stream": (_i, [_vp, _vp]),
+    "tc_sync": (_i, [_vp]),
     "tc_reset": (_i, [_vp, _i]),
     "tc_set_hash_evaluator": (_i, [_vp, _u64, _i, _i]),
     "tc_set_evaluator": (_i, [_vp, _i]),

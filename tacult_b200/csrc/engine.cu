@@ -312,6 +312,13 @@ extern "C" int tc_set_stream(tc_engine *e, void *cuda_stream)
     return TC_OK;
 }
 
+extern "C" int tc_sync(tc_engine *e)
+{
+    TC_TRY(check_engine(e));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    return TC_OK;
+}
+
 extern "C" int tc_reset(tc_engine *e, int env)
 {
     TC_TRY(check_engine(e));

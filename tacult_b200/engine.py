@@ -79,6 +79,9 @@ class Engine:
     def set_stream(self, cuda_stream_ptr):
         check(self.lib.tc_set_stream(self.handle, ctypes.c_void_p(cuda_stream_ptr)))
 
+    def sync(self):
+        check(self.lib.tc_sync(self.handle))
+
     def set_evaluator(self, evaluator):
         check(self.lib.tc_set_evaluator(self.handle, int(evaluator)))
 
@@ -204,6 +207,23 @@ class Engine:
         n = ctypes.c_int(0)
         check(self.lib.tc_selfplay_drain(self.handle, cap, ptr(buf), ctypes.byref(n)))
         return buf[:n.value].copy()
+
+
+    def selfplay_drain_dev(self, out_dev_ptr, capacity):
+        """Finished-game records -> a caller-owned DEVICE buffer of `capacity` tc_example slots (no host copy of the
+        records: only the count crosses).  Returns the number of records written."""
+        n = ctypes.c_int(0)
+        check(self.lib.tc_selfplay_drain_dev(self.handle, int(capacity), ctypes.c_void_p(int(out_dev_ptr)),
+                                             ctypes.byref(n)))
+        return n.value
+
+    def examples_from_records_dev(self, n_out, records_dev_ptr, n_records, index_dev_ptr, obs_dev_ptr, pi_dev_ptr,
+                                  z_dev_ptr):
+        """Training examples (8 symmetries, pi, z) from device-resident records, on the engine's stream."""
+        check(self.lib.tc_examples_from_records_dev(
+            self.handle, int(n_out), ctypes.c_void_p(int(records_dev_ptr)), int(n_records),
+            ctypes.c_void_p(int(index_dev_ptr)) if index_dev_ptr else None, ctypes.c_void_p(int(obs_dev_ptr)),
+            ctypes.c_void_p(int(pi_dev_ptr)), ctypes.c_void_p(int(z_dev_ptr))))
 
 
 # -- stateless rules hooks ---------------------------------------------------------------------

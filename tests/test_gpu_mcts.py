@@ -171,18 +171,21 @@ def test_partitioned_engine_gives_the_same_counts(parts, monkeypatch):
     assert (c1[active == 0] == 0).all() and c1[active == 1].sum() > 0
 
 
-def test_record_replay_with_network_evaluator(make_args):
-    """Identical evaluator outputs, real network: the engine logs every leaf (state, pi, v) its fp32 ResNet
-    produced; the oracle search replays those exact float32 values and must reach the same visit counts."""
+@pytest.mark.parametrize("mode,arch,tol", [("f32", (16, 2, 64), 1e-3), ("bf16", (32, 3, 256), 2e-2)])
+def test_record_replay_with_network_evaluator(make_args, mode, arch, tol):
+    """Identical evaluator outputs, real network: the engine logs every leaf (state, pi, v) its ResNet produced — the
+    fp32 CUDA-core chain or the production bf16 chain (fused tcgen05 trunk -> split-K fc1 -> tensor-core heads); the
+    oracle search replays those exact float32 values and must reach the same visit counts.  This pins the search
+    bookkeeping around the production evaluator (leaf compaction, row routing, counter pair), not only its forward."""
     envs, sims = 6, 40
-    sd = resnet_oracle.make_state_dict(11, channels=16, num_residual_blocks=2, embedding_size=64)
+    sd = resnet_oracle.make_state_dict(11, channels=arch[0], num_residual_blocks=arch[1], embedding_size=arch[2])
 
     class Net:                     # the shape tacult_b200.VectorizedMCTS expects: .nnet.state_dict()
         class nnet:
             @staticmethod
             def state_dict():
                 return sd
-    args = make_args(numEnvs=envs, numMCTSSims=sims, cpuct=2.4, tc_eval_log_capacity=envs * sims * 20, tc_evaluator="f32")
+    args = make_args(numEnvs=envs, numMCTSSims=sims, cpuct=2.4, tc_eval_log_capacity=envs * sims * 20, tc_evaluator=mode)
     game = OracleGame()
     gpu = tb.VectorizedMCTS(game, Net(), args)
     boards = [game.getInitBoard() for _ in range(envs)]
@@ -207,7 +210,32 @@ def test_record_replay_with_network_evaluator(make_args):
         for _ in range(sims):
             cpu.search(canon)
         assert (cpu.root_counts(canon) == counts).all()
-    # and the logged evaluations themselves are the reference network's, to fp32 tolerance
+    # and the logged evaluations themselves are the reference network's, to the mode's tolerance
     obs = np.stack([np.asarray(GameState.from_packed(s).get_obs()).reshape(4, 9, 9) for s in states[:256]])
     rpi, rv = resnet_oracle.forward(sd, obs)
-    assert np.abs(rpi.numpy() - pi[:256]).max() < 1e-3 and np.abs(rv.numpy().ravel() - v[:256]).max() < 1e-3
+    assert np.abs(rpi.numpy() - pi[:256]).max() < tol and np.abs(rv.numpy().ravel() - v[:256]).max() < tol
+
+
+def test_set_roots_fields_form_equals_packed_form():
+    """tc_set_roots takes the GAMESTATE members (uint16 board[9], occ[9], int8 last_square) as the reference holds them
+    (utac_game.py:101-106); it must plant the same roots as tc_set_roots_packed."""
+    n = 96
+    res = tb.rules_playouts(21, 0, n, max_plies=25)
+    roots = np.array([list(r.final_state) for r in res], dtype=np.uint32)
+    board = np.zeros((n, 9), dtype=np.uint16)
+    occ = np.zeros((n, 9), dtype=np.uint16)
+    for i in range(9):
+        board[:, i] = (roots[:, i // 3] >> (9 * (i % 3))) & 0x1FF
+        occ[:, i] = (roots[:, 3 + i // 3] >> (9 * (i % 3))) & 0x1FF
+    last = (roots[:, 6] & 0xF).astype(np.int8) - 1
+    active = (np.arange(n) % 5 != 0).astype(np.uint8)
+    a = tb.Engine(n, 30 * 4 + 64, hash_salt=3)
+    a.set_roots_packed(roots, active)
+    a.search(30, 2.4)
+    b = tb.Engine(n, 30 * 4 + 64, hash_salt=3)
+    b.set_roots_fields(board, occ, last, active)
+    b.search(30, 2.4)
+    ca, cb = a.root_counts(), b.root_counts()
+    assert np.array_equal(ca, cb) and np.array_equal(a.root_q().view(np.uint64), b.root_q().view(np.uint64))
+    live = tb.rules_status(roots) == 0
+    assert (ca[(active == 1) & live].sum(1) == 29).all() and (ca[active == 0] == 0).all()

@@ -135,3 +135,36 @@ def test_selfplay_driver_generates_numenvs_games():
     recs, stats = drv.play_records(seed=3)
     assert stats["games_finished"] == 16 and len(recs) == stats["plies"]      # exactly numEnvs games (coach.py:175)
     assert sorted(set(recs["env"])) == list(range(16))
+
+
+def test_device_drain_and_example_kernel_match_the_host_path():
+    """tc_selfplay_drain_dev leaves the records in HBM and tc_examples_from_records_dev builds (obs, pi, z) with the
+    eight symmetries there; both must equal the host path (tc_selfplay_drain + records_to_arrays, itself checked
+    against getSymmetries above) bit for bit — for all examples in order and for an arbitrary index list."""
+    import torch
+    from tacult_b200.distributed import DeviceReplay, DeviceTrajectoryExchange
+    from tacult_b200.selfplay import records_to_arrays
+    envs, sims, threshold, salt = 24, 12, 6, 41
+    _, host_recs = run_games(envs, sims, threshold, seed=13, salt=salt)
+    eng = tb.Engine(envs, sims * 82 + 64, hash_salt=salt)
+    eng.selfplay_begin(sims, 2.4, threshold, seed=13, auto_reset=False)
+    eng.selfplay_step(81)
+    eng.selfplay_sync()
+    ex = DeviceTrajectoryExchange(eng, "cuda:0")
+    recs_dev, counts = ex.gather()
+    assert counts == [len(host_recs)] and recs_dev.is_cuda
+    got = recs_dev.cpu().numpy().reshape(-1).view(tb._lib.EXAMPLE_DTYPE)
+    assert got.tobytes() == host_recs.tobytes()
+    assert eng.selfplay_drain_dev(ex.send.data_ptr(), ex.capacity) == 0          # drained
+    replay = DeviceReplay(eng, recs_dev)
+    obs, pi, z = (t.cpu().numpy() for t in replay.examples())
+    want_obs, want_pi, want_z = records_to_arrays(host_recs, augment=True)
+    assert np.array_equal(obs, want_obs) and np.array_equal(pi, want_pi) and np.array_equal(z, want_z)
+    idx = torch.from_numpy(np.random.RandomState(0).randint(0, replay.n_examples, size=1000)).cuda()
+    obs, pi, z = (t.cpu().numpy() for t in replay.examples(idx))
+    k = idx.cpu().numpy()
+    assert np.array_equal(obs, want_obs[k]) and np.array_equal(pi, want_pi[k]) and np.array_equal(z, want_z[k])
+    # a draw's z is +-1e-4 and tau=0 rows are one-hot on the move played
+    assert set(np.unique(np.abs(want_z))) <= {np.float32(1.0), np.float32(1e-4)}
+    onehot = host_recs["tau_one"] == 0
+    assert (pi.shape[1] == 81) and np.array_equal(want_pi[::8][onehot].argmax(1), host_recs["action"][onehot])

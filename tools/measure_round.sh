@@ -11,12 +11,12 @@ timeout 300 python tools/eval_sweep.py --net deep --batches 256,1024,4096,16384,
 timeout 300 python tools/eval_sweep.py --net trainer --batches 256,1024,4096,16384,65536 > gpurun_out/sweep_trainer_$TAG.jsonl 2>&1; echo "trainer sweep rc=$?"
 timeout 200 python tools/arena_bench.py > gpurun_out/arena_$TAG.json 2>&1; echo "arena rc=$?"
 # launch list of a short bench run (per-launch durations are cold-cache and serialised: shares, not absolutes)
-timeout 200 python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --profile-plies 0 > gpurun_out/plain_short.log 2>&1; echo "short plain rc=$?"
+timeout 200 python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --skip-extras --profile-plies 0 > gpurun_out/plain_short.log 2>&1; echo "short plain rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --profile-plies 0 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launch list rc=$?"
+    python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --skip-extras --profile-plies 0 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launch list rc=$?"
 # one full capture per hot kernel (skip the warm-up launches)
 for K in k_trunk_fused k_backup_select k_fc1_splitk k_gemm_tc; do
   timeout 900 ncu --set full --import-source on --clock-control none -k regex:$K -s 300 -c 1 -f -o gpurun_out/prof_${K}_$TAG \
-      python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --profile-plies 0 > gpurun_out/ncu_$K.log 2>&1; echo "ncu $K rc=$?"
+      python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --skip-extras --profile-plies 0 > gpurun_out/ncu_$K.log 2>&1; echo "ncu $K rc=$?"
 done
 tail -1 gpurun_out/bench_$TAG.log | cut -c1-300
