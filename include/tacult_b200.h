@@ -48,7 +48,11 @@ enum {
 enum {
     TC_EVAL_NET_F32 = 0,   /* fp32 CUDA-core forward: parity mode, 1e-3 of the reference net */
     TC_EVAL_NET_BF16 = 1,  /* bf16 tcgen05/TMEM trunk: production mode, 2e-2 */
-    TC_EVAL_HASH = 2       /* deterministic integer-hash priors/values: bit-exact visit-count tests */
+    TC_EVAL_HASH = 2,      /* deterministic integer-hash priors/values: bit-exact visit-count tests */
+    TC_EVAL_NET_BF16_MASKED = 3   /* bf16 chain whose policy head masks the soft-max with the leaf's legal moves and
+                                     renormalises in float32 (the composition mcts.py:272-275 applies in float64 to the
+                                     unmasked output); the tree stores those priors as they come.  Production mode:
+                                     2e-2 of the reference priors, not bit-identical to parity mode. */
 };
 
 /* terminal status of a canonical position, seen by its side to move */

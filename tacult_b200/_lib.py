@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libtacult_b200.so")
 
 ABI_VERSION = 2
 TC_OK, TC_EINVAL, TC_ECUDA, TC_ECAPACITY, TC_ESTATE, TC_EILLEGAL = 0, -1, -2, -3, -4, -5
-EVAL_NET_F32, EVAL_NET_BF16, EVAL_HASH = 0, 1, 2
+EVAL_NET_F32, EVAL_NET_BF16, EVAL_HASH, EVAL_NET_BF16_MASKED = 0, 1, 2, 3
 LIVE, LOST, DRAW, WON = 0, 1, 2, 3
 ACTIONS = 81
 STATE_WORDS = 8

@@ -159,8 +159,8 @@ extern "C" int tc_create(const tc_config *cfg, tc_engine **out)
     TC_CHECK(cfg->num_envs >= 1, TC_EINVAL, "num_envs must be >= 1");
     TC_CHECK(cfg->max_nodes_per_tree >= 2 && (uint32_t)cfg->max_nodes_per_tree <= MAX_NODES_PER_TREE, TC_EINVAL,
              "max_nodes_per_tree out of range [2, %u]", MAX_NODES_PER_TREE);
-    TC_CHECK(cfg->evaluator >= TC_EVAL_NET_F32 && cfg->evaluator <= TC_EVAL_HASH, TC_EINVAL, "unknown evaluator %d",
-             cfg->evaluator);
+    TC_CHECK(cfg->evaluator >= TC_EVAL_NET_F32 && cfg->evaluator <= TC_EVAL_NET_BF16_MASKED, TC_EINVAL,
+             "unknown evaluator %d", cfg->evaluator);
     int ndev = 0;
     TC_CUDA(cudaGetDeviceCount(&ndev));
     TC_CHECK(cfg->device >= 0 && cfg->device < ndev, TC_EINVAL, "device %d not present (%d visible)", cfg->device, ndev);
@@ -342,7 +342,8 @@ extern "C" int tc_set_hash_evaluator(tc_engine *e, uint64_t salt, int pi_levels,
 extern "C" int tc_set_evaluator(tc_engine *e, int evaluator)
 {
     TC_TRY(check_engine(e));
-    TC_CHECK(evaluator >= TC_EVAL_NET_F32 && evaluator <= TC_EVAL_HASH, TC_EINVAL, "unknown evaluator %d", evaluator);
+    TC_CHECK(evaluator >= TC_EVAL_NET_F32 && evaluator <= TC_EVAL_NET_BF16_MASKED, TC_EINVAL, "unknown evaluator %d",
+             evaluator);
     e->evaluator = evaluator;
     return TC_OK;
 }
@@ -392,6 +393,7 @@ static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st
     // slot for simulation sim + 1, so no memset node sits between the kernels of the chain (they are launched with
     // programmatic stream serialisation, common.cuh)
     TreeStore ts = e->hts[h];
+    ts.priors_masked = e->evaluator == TC_EVAL_NET_BF16_MASKED;
     int *pair = ts.eval_count;
     ts.eval_count = pair + (sim & 1);
     ts.eval_count_next = pair + ((sim + 1) & 1);
@@ -411,7 +413,8 @@ static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st
     } else if (e->evaluator == TC_EVAL_NET_F32) {
         e->launches += n32.forward(ts.E, ts.eval_count, ts.eval_state, nullptr, ts.eval_pi, ts.eval_v, nullptr, st, &e->prof);
     } else {
-        int n = n16.forward(ts.E, ts.eval_count, ts.eval_state, nullptr, ts.eval_pi, ts.eval_v, nullptr, st, &e->prof);
+        int n = n16.forward(ts.E, ts.eval_count, ts.eval_state, nullptr, ts.eval_pi, ts.eval_v, nullptr, st, &e->prof,
+                            ts.priors_masked);
         if (n < 0) return n;
         e->launches += n;
     }
@@ -476,7 +479,7 @@ static int check_evaluator_ready(tc_engine *e)
 {
     if (e->evaluator == TC_EVAL_HASH) return TC_OK;
     TC_CHECK(e->have_weights, TC_ESTATE, "network evaluator selected but tc_load_weights has not been called");
-    if (e->evaluator == TC_EVAL_NET_BF16)
+    if (e->evaluator == TC_EVAL_NET_BF16 || e->evaluator == TC_EVAL_NET_BF16_MASKED)
         TC_CHECK(e->net16.loaded, TC_ESTATE, "bf16 evaluator not available for this network shape: %s",
                  e->net16.why_not.c_str());
     return TC_OK;
@@ -603,8 +606,10 @@ static int run_forward(tc_engine *e, int evaluator, int batch, const uint32_t *s
                        float *pi_dev, float *v_dev, float *logits_dev)
 {
     TC_CHECK(e->have_weights, TC_ESTATE, "tc_forward: tc_load_weights has not been called");
-    TC_CHECK(evaluator == TC_EVAL_NET_F32 || evaluator == TC_EVAL_NET_BF16, TC_EINVAL,
-             "tc_forward: evaluator must be TC_EVAL_NET_F32 or TC_EVAL_NET_BF16");
+    TC_CHECK(evaluator == TC_EVAL_NET_F32 || evaluator == TC_EVAL_NET_BF16 || evaluator == TC_EVAL_NET_BF16_MASKED, TC_EINVAL,
+             "tc_forward: evaluator must be TC_EVAL_NET_F32, TC_EVAL_NET_BF16 or TC_EVAL_NET_BF16_MASKED");
+    TC_CHECK(evaluator != TC_EVAL_NET_BF16_MASKED || (states_dev && !logits_dev), TC_EINVAL,
+             "the masked policy needs packed positions (tc_forward_states*) and no logits output");
     TC_CHECK(states_dev == nullptr || e->folded.d.in_planes == 4, TC_EINVAL,
              "packed positions imply 4 input planes, the loaded network has %d", e->folded.d.in_planes);
     // the network scratch is sized for num_envs rows: run larger batches in slices
@@ -619,7 +624,8 @@ static int run_forward(tc_engine *e, int evaluator, int batch, const uint32_t *s
         } else {
             TC_CHECK(e->net16.loaded, TC_ESTATE, "bf16 evaluator not available for this network shape: %s",
                      e->net16.why_not.c_str());
-            int n = e->net16.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream, &e->prof);
+            int n = e->net16.forward(nb, nullptr, s, o, pi_dev + (size_t)r0 * 81, v_dev + r0, lg, e->stream, &e->prof,
+                                     evaluator == TC_EVAL_NET_BF16_MASKED);
             if (n < 0) return n;
             e->launches += n;
         }

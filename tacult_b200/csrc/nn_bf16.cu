@@ -543,6 +543,9 @@ struct NetBF16Impl {
     std::vector<CUtensorMap> map_conv_w;
     int conv_stages = 4, fc1_stages = 4, fc1_block_n = 64;
     bool fc1_split_k = true;               // K split over a CTA pair (nn_fc1.cu); TACULT_FC1_SPLITK=0 disables
+    bool fc1_heads = false;                // fc1 and the heads in one launch (k_fc1_heads); TACULT_FC1_HEADS=0 disables
+    int fc1_heads_stages = 3;
+    DevBuf<int> tile_ready;                // arrival counter per 128-row tile, zero between launches
     size_t side_smem_budget = 96 * 1024;       // what an fc1 / heads CTA may use next to a resident fused-trunk CTA
     int sm_count = SM_COUNT;
 };
@@ -673,6 +676,18 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
         if (fb && atoi(fb) > 0 && E % atoi(fb) == 0 && atoi(fb) % 32 == 0 && atoi(fb) <= 256) m.fc1_block_n = atoi(fb);
         const char *sk = getenv("TACULT_FC1_SPLITK");
         m.fc1_split_k = !sk || atoi(sk) != 0;
+    }
+    {
+        const char *fh = getenv("TACULT_FC1_HEADS");
+        // single-partition engines only: the fused kernel takes half of an SM's TMEM columns and ~87 KB of shared memory
+        m.fc1_heads = (!fh || atoi(fh) != 0) && !share_sm && m.fc1_split_k && m.heads_on_tensor && m.fc1_block_n == 64;
+        if (m.fc1_heads) {
+            TC_CUDA(m.tile_ready.alloc((size_t)(cap + 127) / 128 + 1));
+            TC_CUDA(cudaMemset(m.tile_ready.p, 0, m.tile_ready.bytes()));
+            m.fc1_heads_stages = 3;
+            if (const char *fs = getenv("TACULT_FC1_HEADS_STAGES"))
+                if (atoi(fs) >= 2 && atoi(fs) <= 6) m.fc1_heads_stages = atoi(fs);
+        }
     }
     TC_TRY(make_map(&m.map_flat, m.flat.p, (uint64_t)flat_rows, (uint64_t)81 * C, 128, 64));
     TC_TRY(make_map(&m.map_fc1, m.fc1_w.p, (uint64_t)E, (uint64_t)81 * C, (uint32_t)m.fc1_block_n, 64));
@@ -853,7 +868,7 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
 }
 
 int NetBF16::forward(int batch, const int *count_dev, const uint32_t *states, const float *obs, float *pi, float *v,
-                     float *logits, cudaStream_t st, Profiler *prof)
+                     float *logits, cudaStream_t st, Profiler *prof, int masked)
 {
     if (!loaded || !impl) {
         set_error("bf16 evaluator: %s", why_not.c_str());
@@ -865,6 +880,19 @@ int NetBF16::forward(int batch, const int *count_dev, const uint32_t *states, co
     int launches = 0;
     const int C = m.d.channels, E = m.d.embedding_size;
     run_trunk(m, batch, count_dev, states, obs, 2 * m.d.num_residual_blocks, true, st, prof, launches);
+    if (m.fc1_heads && !logits) {
+        prof->begin(TC_K_NN_FC1, st);
+        TC_TRY(launch_fc1_heads(m.map_flat, m.map_fc1, m.map_emb16, m.map_head_w, batch, count_dev, 81 * C, E,
+                                m.fc1_heads_stages, m.fc1_b.p, m.emb16.p, m.tile_ready.p, m.head_b96.p, pi, v,
+                                masked ? states : nullptr, masked && states, st));
+        prof->end(st);
+        return launches + 1;
+    }
+    if (masked) {
+        set_error("the masked soft-max needs the fused fc1+heads kernel (single partition, embedding a multiple of 64, "
+                  "TACULT_FC1_HEADS not 0)");
+        return TC_ESTATE;
+    }
     GemmParams P{};
     P.count_dev = count_dev;
     P.batch = batch;

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(128) k_selfplay_move(TreeStore ts, SelfPlaySto
         rec->tau_one = tau_one ? 1 : 0;
         rec->player = (int8_t)e.player;
         rec->z_sign = 0;
+        reinterpret_cast<uint16_t *>(rec)[99] = 0;      // the two padding bytes at offset 198: records compare bytewise
         rec->env = env;
         rec->game = e.game;
         rec->ply = e.ply;

@@ -505,7 +505,8 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
             m[q] = 0.0;
             if (a < 81 && ((am[q] >> lane) & 1u)) m[q] = (double)pi[a];
         }
-        double total = numpy_sum81(m, lane);
+        // production mode: the policy head already masked and renormalised (float32); parity mode: mcts.py:272-275
+        const double total = ts.priors_masked ? 1.0 : numpy_sum81(m, lane);
         EdgeBlock eb = edge_block(ts, tree, off, n);
         const bool ok = total > 0.0;
         const double uniform = __ddiv_rn(1.0, (double)n);     // (0 + valids) / np.sum(valids), mcts.py:282-283
@@ -513,7 +514,7 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
         for (int q = 0; q < 3; ++q) {
             if ((am[q] >> lane) & 1u) {
                 int j = edge_index(am, q, lane);
-                eb.P[j] = ok ? __ddiv_rn(m[q], total) : uniform;
+                eb.P[j] = ts.priors_masked ? m[q] : (ok ? __ddiv_rn(m[q], total) : uniform);
             }
         }
         x = (double)ts.eval_v[row];

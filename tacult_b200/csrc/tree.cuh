@@ -65,6 +65,7 @@ struct TreeStore {
     int *eval_count;
     int *eval_count_next;       // counter of the NEXT simulation, zeroed by this one's descent kernel (or null)
     int *error_flag;
+    int priors_masked;          // eval_pi is already masked + renormalised (TC_EVAL_NET_BF16_MASKED): store it as is
 };
 
 struct EdgeBlock {

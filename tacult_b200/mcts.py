@@ -81,7 +81,7 @@ class VectorizedMCTS:
         module = getattr(nnet, "nnet", nnet)    # NNetWrapper.nnet (nn_wrapper.py:27) or a bare module
         self.engine.load_weights(module.state_dict())
         mode = str(_opt(args, "tc_evaluator", "f32")).lower()
-        self.engine.set_evaluator(_lib.EVAL_NET_BF16 if mode == "bf16" else _lib.EVAL_NET_F32)
+        self.engine.set_evaluator({"bf16": _lib.EVAL_NET_BF16, "bf16_masked": _lib.EVAL_NET_BF16_MASKED}.get(mode, _lib.EVAL_NET_F32))
 
     def refresh_weights(self):
         """Call after the wrapped network's weights changed (e.g. load_checkpoint, coach.py:35,256)."""

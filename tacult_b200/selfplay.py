@@ -70,7 +70,8 @@ class SelfPlayDriver:
             module = getattr(nnet, "nnet", nnet)
             self.engine.load_weights(module.state_dict())
             mode = str(args.get("tc_evaluator", "bf16") if hasattr(args, "get") else "bf16").lower()
-            self.engine.set_evaluator(_lib.EVAL_NET_BF16 if mode == "bf16" else _lib.EVAL_NET_F32)
+            self.engine.set_evaluator({"bf16": _lib.EVAL_NET_BF16,
+                                       "bf16_masked": _lib.EVAL_NET_BF16_MASKED}.get(mode, _lib.EVAL_NET_F32))
 
     def play_records(self, seed=0, max_plies=81):
         """Plays numEnvs games to the end; returns the raw trajectory records and the self-play statistics."""

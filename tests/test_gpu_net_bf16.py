@@ -120,3 +120,70 @@ def test_search_with_bf16_evaluator():
     assert (counts.sum(1) == 63).all() and (counts == counts[0]).all()
     st = eng.stats()
     assert st["nn_leaves"] + st["terminal_leaves"] == 512 * 64
+
+
+def test_fused_fc1_heads_equals_the_separate_kernels(monkeypatch):
+    """k_fc1_heads (fc1 and the policy/value heads in one launch, the last-arriving cluster of a row tile runs its heads)
+    must give the very bits of k_fc1_splitk -> k_gemm_tc<HEADS>: same operand chunks, same accumulation order."""
+    sd = torch_default_state_dict(19, 32, 3, 256)
+    rng = np.random.RandomState(2)
+    res = tb.rules_playouts(9, 0, 3000, max_plies=40)
+    states = np.array([list(r.final_state) for r in res], dtype=np.uint32)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TACULT_FC1_HEADS", flag)       # read when the weights are uploaded
+        eng = tb.Engine(3000, 2)
+        eng.load_weights(sd)
+        out[flag] = [eng.forward_states(states[:b], BF16) for b in (3000, 1, 127, 128, 129, 1000, 2049)]
+        out[flag].append(eng.forward_states(states, BF16))            # a second launch: the arrival counters were reset
+    for (p1, v1), (p0, v0) in zip(out["1"], out["0"]):
+        assert np.array_equal(p1, p0) and np.array_equal(v1, v0)
+    assert np.array_equal(out["1"][0][0], out["1"][-1][0])
+    rpi, rv = resnet_oracle.forward(sd, obs_of(states[:512]))
+    assert np.abs(out["1"][0][0][:512] - rpi.numpy()).max() < TOL_BF16
+
+
+def test_masked_policy_head_is_softmax_mask_renormalise():
+    """Production mode (TC_EVAL_NET_BF16_MASKED): the heads epilogue masks the soft-max with the leaf's legal moves and
+    renormalises — the composition mcts.py:272-275 applies to the unmasked output — within 2e-2 of the reference."""
+    sd = torch_default_state_dict(23, 32, 3, 256)
+    res = tb.rules_playouts(4, 0, 2000, max_plies=60)
+    states = np.array([list(r.final_state) for r in res], dtype=np.uint32)
+    states = states[tb.rules_status(states) == 0]
+    eng = tb.Engine(len(states), 2)
+    eng.load_weights(sd)
+    pi, v = eng.forward_states(states, tb._lib.EVAL_NET_BF16_MASKED)
+    upi, uv = eng.forward_states(states, BF16)
+    legal = tb.rules_legal_mask(states).astype(bool)
+    assert (pi[~legal] == 0).all() and np.allclose(pi.sum(1), 1.0, atol=1e-5) and np.array_equal(v, uv)
+    rpi, rv = resnet_oracle.forward(sd, obs_of(states))
+    want = rpi.numpy().astype(np.float64) * legal
+    want /= want.sum(1, keepdims=True)
+    assert np.abs(pi - want).max() < TOL_BF16 and np.abs(v - rv.numpy().ravel()).max() < TOL_BF16
+    # and it is the engine's own unmasked output, masked and renormalised
+    own = upi.astype(np.float64) * legal
+    own /= own.sum(1, keepdims=True)
+    assert np.abs(pi - own).max() < 1e-5
+
+
+def test_search_in_production_mode_keeps_its_invariants():
+    sd = torch_default_state_dict(29, 32, 3, 256)
+    n, sims = 512, 64
+    res = tb.rules_playouts(6, 0, n, max_plies=30)
+    roots = np.array([list(r.final_state) for r in res], dtype=np.uint32)
+    live = tb.rules_status(roots) == 0
+    counts = {}
+    for mode in (BF16, tb._lib.EVAL_NET_BF16_MASKED):
+        eng = tb.Engine(n, sims * 4 + 64)
+        eng.load_weights(sd)
+        eng.set_evaluator(mode)
+        eng.set_roots_packed(roots)
+        eng.search(sims, 2.4)
+        counts[mode] = eng.root_counts()
+        st = eng.stats()
+        assert st["nn_leaves"] + st["terminal_leaves"] == int(live.sum()) * sims
+        assert (counts[mode][live].sum(1) == sims - 1).all() and (counts[mode][~live] == 0).all()
+        assert (counts[mode][~tb.rules_legal_mask(roots).astype(bool)] == 0).all()
+    # float32 vs float64 renormalisation only moves priors in the last bits: the visit counts agree almost everywhere
+    same = (counts[BF16] == counts[tb._lib.EVAL_NET_BF16_MASKED]).all(1).mean()
+    assert same > 0.9, same
