@@ -200,6 +200,10 @@ int tc_forward_states(tc_engine *e, int evaluator, int batch, const uint32_t *st
 int tc_forward_states_dev(tc_engine *e, int evaluator, int batch, const uint32_t *states_dev, float *pi_dev,
                           float *v_dev);
 
+/* the same from dense observation planes already in HBM: obs_dev[B][in_planes][9][9] float32 (any in_planes <= 32, e.g. the
+ * 8-frame history variant) */
+int tc_forward_obs_dev(tc_engine *e, int evaluator, int batch, const float *obs_dev, float *pi_dev, float *v_dev);
+
 /* test hook: trunk activations after conv_in and the first n_convs residual-block convolutions,
  * float32 [batch][81][channels] (NHWC), for either network evaluator */
 int tc_debug_trunk(tc_engine *e, int evaluator, int batch, const uint32_t *states_host, int n_convs, float *out_host);

@@ -155,6 +155,7 @@ SYMBOLS = {
     "tc_forward": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "tc_forward_states": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "tc_forward_states_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "tc_forward_obs_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "tc_debug_trunk": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "tc_selfplay_begin": (_i, [_vp, ctypes.POINTER(SelfPlayConfig)]),
     "tc_selfplay_configure": (_i, [_vp, ctypes.POINTER(SelfPlayConfig)]),

@@ -79,6 +79,19 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // completed and its memory is visible; in a normally launched kernel it is a no-op.  No kernel here triggers its
 // dependents early: waiting CTAs would hold shared memory the other partition's kernels need.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next kernel of the chain start launching now: its CTAs become resident as soon as an SM has room for them, run
+// their prologue and park in griddep_wait() until THIS grid has completed (correctness never depends on the trigger).
+// Opt-in (TACULT_PDL_TRIGGER=1): parked CTAs hold registers / shared memory.
+__device__ __forceinline__ void griddep_launch(int on)
+{
+    if (on) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline int pdl_trigger_enabled()
+{
+    static const int on = [] { const char *v = getenv("TACULT_PDL_TRIGGER"); return v ? atoi(v) : 0; }();
+    return on;
+}
 
 inline bool pdl_enabled()
 {

@@ -394,6 +394,7 @@ static int enqueue_simulation(tc_engine *e, double cpuct, int h, cudaStream_t st
     // programmatic stream serialisation, common.cuh)
     TreeStore ts = e->hts[h];
     ts.priors_masked = e->evaluator == TC_EVAL_NET_BF16_MASKED;
+    ts.pdl_trigger = pdl_trigger_enabled();
     int *pair = ts.eval_count;
     ts.eval_count = pair + (sim & 1);
     ts.eval_count_next = pair + ((sim + 1) & 1);
@@ -679,6 +680,14 @@ extern "C" int tc_forward_states_dev(tc_engine *e, int evaluator, int batch, con
              "tc_forward_states_dev: null buffer");
     if (batch == 0) return TC_OK;
     return run_forward(e, evaluator, batch, states_dev, nullptr, pi_dev, v_dev, nullptr);
+}
+
+extern "C" int tc_forward_obs_dev(tc_engine *e, int evaluator, int batch, const float *obs_dev, float *pi_dev, float *v_dev)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(batch >= 0 && (batch == 0 || (obs_dev && pi_dev && v_dev)), TC_EINVAL, "tc_forward_obs_dev: null buffer");
+    if (batch == 0) return TC_OK;
+    return run_forward(e, evaluator, batch, nullptr, obs_dev, pi_dev, v_dev, nullptr);
 }
 
 extern "C" int tc_debug_trunk(tc_engine *e, int evaluator, int batch, const uint32_t *states_host, int n_convs,

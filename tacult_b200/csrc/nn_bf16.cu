@@ -409,8 +409,11 @@ __global__ void __launch_bounds__(256) k_stem_bf16(int batch, const int *__restr
     }
 }
 
-// Observation planes as a 16-channel bf16 activation in the padded layout (channels >= in_planes are zero), so
-// that conv_in runs through the same tensor-core implicit GEMM as the trunk (K = 16 per tap).  One warp per position.
+// Observation planes as a PC-channel (16 or 32) bf16 activation in the padded layout (channels >= in_planes are zero),
+// so that conv_in runs through the same tensor-core implicit GEMM as the trunk (K = PC per tap).  One warp per position.
+// 32 channels hold the 8-frame history variant (8 x 4 planes, BASELINE.json configs[4]); the reference has 4 planes
+// (network.py:55).
+template <int PC>
 __global__ void __launch_bounds__(256) k_encode_planes_bf16(int batch, const int *__restrict__ count_dev,
                                                             const uint32_t *__restrict__ states,
                                                             const float *__restrict__ obs, int in_planes,
@@ -432,9 +435,9 @@ __global__ void __launch_bounds__(256) k_encode_planes_bf16(int batch, const int
     for (int q = 0; q < 3; ++q) {
         const int a = lane + 32 * q;
         if (a >= 81) continue;
-        float v[16];
+        float v[PC];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = 0.f;
+        for (int c = 0; c < PC; ++c) v[c] = 0.f;
         if (states) {
             const bool mine = action_bit(p.mine, a), occ = action_bit(p.occ, a);
             v[0] = mine ? 1.f : 0.f;
@@ -443,16 +446,16 @@ __global__ void __launch_bounds__(256) k_encode_planes_bf16(int batch, const int
             v[3] = 1.f;
         } else {
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
+            for (int c = 0; c < PC; ++c)
                 if (c < in_planes) v[c] = obs[((size_t)row * in_planes + c) * 81 + a];
         }
-        uint4 o[2];
+        uint4 o[PC / 8];
         __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(o);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) op[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
-        uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)PAD0 + (size_t)row * ROWS_PER_POS + (a / 9) * 10 + a % 9) * 16);
-        dst[0] = o[0];
-        dst[1] = o[1];
+        for (int c = 0; c < PC / 2; ++c) op[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+        uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)PAD0 + (size_t)row * ROWS_PER_POS + (a / 9) * 10 + a % 9) * PC);
+#pragma unroll
+        for (int c = 0; c < PC / 8; ++c) dst[c] = o[c];
     }
 }
 
@@ -523,7 +526,8 @@ struct NetBF16Impl {
     CUtensorMap map_emb16, map_head_w;
     bool heads_on_tensor = false;
     DevBuf<float> stem_w, stem_b;
-    DevBuf<__nv_bfloat16> planes;          // padded layout, 16 channels (observation planes, zero padded)
+    DevBuf<__nv_bfloat16> planes;          // padded layout, stem_k channels (observation planes, zero padded)
+    int stem_k = 16;                       // 16 (up to 16 planes) or 32 (the 8-frame history variant, 32 planes)
     DevBuf<__nv_bfloat16> stem_w16;        // [9][C][16]
     CUtensorMap map_planes, map_stem_w;
     bool stem_on_tensor = false;
@@ -634,19 +638,21 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
         TC_TRY(make_map(&m.map_act[i], m.act[i].p, m.act_rows, C, 128, (uint32_t)m.block_k));
         if (C <= 64) TC_TRY(make_map(&m.map_act_sh[i], m.act[i].p, m.act_rows, C, SH_ROWS, (uint32_t)m.block_k));
     }
-    m.stem_on_tensor = I <= 16;
+    m.stem_on_tensor = I <= 32;
+    m.stem_k = I <= 16 ? 16 : 32;
     if (m.stem_on_tensor) {
-        std::vector<__nv_bfloat16> sw((size_t)9 * C * 16, __float2bfloat16_rn(0.f));
+        const int SK = m.stem_k;
+        std::vector<__nv_bfloat16> sw((size_t)9 * C * SK, __float2bfloat16_rn(0.f));
         for (int tap = 0; tap < 9; ++tap)
             for (int co = 0; co < C; ++co)
                 for (int ci = 0; ci < I; ++ci)
-                    sw[((size_t)tap * C + co) * 16 + ci] = __float2bfloat16_rn(f.stem_w[((size_t)co * I + ci) * 9 + tap]);
+                    sw[((size_t)tap * C + co) * SK + ci] = __float2bfloat16_rn(f.stem_w[((size_t)co * I + ci) * 9 + tap]);
         TC_TRY(upload(m.stem_w16, sw));
-        TC_CUDA(m.planes.alloc(m.act_rows * 16));
+        TC_CUDA(m.planes.alloc(m.act_rows * SK));
         TC_CUDA(cudaMemset(m.planes.p, 0, m.planes.bytes()));
-        TC_TRY(make_map(&m.map_planes, m.planes.p, m.act_rows, 16, 128, 16));
-        TC_TRY(make_map(&m.map_planes_sh, m.planes.p, m.act_rows, 16, SH_ROWS, 16));
-        TC_TRY(make_map(&m.map_stem_w, m.stem_w16.p, (uint64_t)9 * C, 16, (uint32_t)C, 16));
+        TC_TRY(make_map(&m.map_planes, m.planes.p, m.act_rows, SK, 128, SK));
+        if (C <= 64) TC_TRY(make_map(&m.map_planes_sh, m.planes.p, m.act_rows, SK, SH_ROWS, SK));
+        TC_TRY(make_map(&m.map_stem_w, m.stem_w16.p, (uint64_t)9 * C, SK, (uint32_t)C, SK));
     }
     const size_t flat_rows = std::max(cap, 128);
     TC_CUDA(m.flat.alloc(flat_rows * 81 * C));
@@ -695,7 +701,7 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
     {
         const char *fz = getenv("TACULT_FUSED");
         int G = 0, T = 0;
-        m.fused = m.stem_on_tensor && (!fz || atoi(fz) != 0) && fused_plan(C, G, T);
+        m.fused = m.stem_on_tensor && I <= 16 && (!fz || atoi(fz) != 0) && fused_plan(C, G, T);
         if (m.fused) {
             // G, T are the largest group that fits.  Size the kernel for THIS instance's capacity instead: the group the
             // kernel would pick for a full batch (it re-balances from the live leaf count, never above these maxima), so
@@ -801,7 +807,8 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
     const bool stem_flat = to_flat && n_convs == 0;
     prof->begin(TC_K_NN_STEM, st);
     if (m.stem_on_tensor) {
-        k_encode_planes_bf16<<<ceil_div(batch, 8), 256, 0, st>>>(batch, count_dev, states, obs, I, m.planes.p);
+        if (m.stem_k == 16) k_encode_planes_bf16<16><<<ceil_div(batch, 8), 256, 0, st>>>(batch, count_dev, states, obs, I, m.planes.p);
+        else k_encode_planes_bf16<32><<<ceil_div(batch, 8), 256, 0, st>>>(batch, count_dev, states, obs, I, m.planes.p);
         GemmParams S{};
         S.count_dev = count_dev;
         S.batch = batch;
@@ -813,14 +820,14 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
         S.a_row0 = PAD0;
         S.b_tap_rows = C;
         S.variant = m.conv_variant;
-        S.stages = pick_stages(16, C, 48 * 1024, S.variant);
+        S.stages = pick_stages(m.stem_k, C, 48 * 1024, S.variant);
         S.mode = stem_flat ? OUT_COMPACT_BF16 : OUT_PADDED_BF16;
         S.relu = 1;
         S.ldc = C;
         S.bias = m.stem_b.p;
         S.residual = nullptr;
         S.out = stem_flat ? (void *)m.flat.p : (void *)m.act[0].p;
-        launch_gemm(m, 16, S.variant ? m.map_planes_sh : m.map_planes, m.map_stem_w, S, (batch * ROWS_PER_POS + 127) / 128, st);
+        launch_gemm(m, m.stem_k, S.variant ? m.map_planes_sh : m.map_planes, m.map_stem_w, S, (batch * ROWS_PER_POS + 127) / 128, st);
         launches += 2;
     } else {
         k_stem_bf16<<<batch, 256, sizeof(float) * I * 121, st>>>(batch, count_dev, states, obs, I, C, m.stem_w.p,

@@ -203,6 +203,7 @@ struct HParams {
     float *v;                // [row]
     const uint32_t *states;  // packed leaf positions (masked mode), else null
     int masked;
+    int pdl_trigger;
 };
 
 __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ CUtensorMap tmA,
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2);
     int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
+    griddep_launch(P.pdl_trigger);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -469,6 +471,7 @@ int launch_fc1_heads(const CUtensorMap &a, const CUtensorMap &b, const CUtensorM
     P.v = v;
     P.states = states;
     P.masked = masked;
+    P.pdl_trigger = pdl_trigger_enabled();
     const size_t smem = fc1_heads_smem(stages);
     static bool attr_set[64] = {false};
     int dev = 0;

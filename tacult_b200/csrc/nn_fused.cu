@@ -50,6 +50,7 @@ struct FusedParams {
     const float *obs;        // dense planes [row][in_planes][81]
     __nv_bfloat16 *out;      // compact [row][81][C] (fc1 input)
     long long *timeline;     // optional: clock64 stamps of CTA 0 (debugging / profiling aid), else null
+    int pdl_trigger;         // griddepcontrol.launch_dependents at kernel entry (common.cuh)
 };
 
 template <int SW>
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
 
     // ---- prologue that depends on nothing the previous kernel wrote: it overlaps that kernel's tail (programmatic
     //      dependent launch, common.cuh) ----
+    griddep_launch(P.pdl_trigger);
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW_stem);
         tma_prefetch_desc(&tmW_conv);
@@ -420,6 +422,7 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
     P.states = states;
     P.obs = obs;
     P.out = out_flat;
+    P.pdl_trigger = pdl_trigger_enabled();
     static long long *timeline_dev = nullptr;
     if (getenv("TACULT_FUSED_TIMELINE")) {
         if (!timeline_dev) cudaMalloc(&timeline_dev, 8 * 64 * sizeof(long long));

@@ -102,6 +102,7 @@ struct Walk {
     int active, leaf_kind, leaf_node, leaf_row;
     double leaf_value;
     uint32_t nn_leaves, sum_leaf_legal;
+    uint32_t leaf_off, leaf_n, leaf_am[3];
 };
 
 // Creates a node for `p` (action mask am) and requests its evaluation.  Returns the node index, or -1 if a
@@ -146,6 +147,9 @@ __device__ int create_leaf(const TreeStore &ts, int tree, Walk &w, const Pos &p,
     w.leaf_kind = LEAF_NN;
     w.leaf_node = (int)idx;
     w.leaf_row = row;
+    w.leaf_off = off;
+    w.leaf_n = n;
+    w.leaf_am[0] = am[0]; w.leaf_am[1] = am[1]; w.leaf_am[2] = am[2];
     w.nn_leaves += 1;
     w.sum_leaf_legal += n;
     return (int)idx;
@@ -260,18 +264,25 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
     w.leaf_value = 0.0;
     w.nn_leaves = 0;
     w.sum_leaf_legal = 0;
+    w.leaf_off = w.leaf_n = 0;
+    w.leaf_am[0] = w.leaf_am[1] = w.leaf_am[2] = 0;
     int root_idx = cp->root_idx;
     uint32_t root_off = cp->root_off, root_n = cp->root_n;
     uint32_t depth = 0, sum_legal = 0, terminal = 0, transp = 0;
     uint2 *path = ts.path + (size_t)tree * MAX_DEPTH;
     const uint4 *hdr = ts.node_hdr + 2ull * (size_t)tree * ts.capN;
 
-    if (root_idx < 0) {
-        // root never expanded: it is this simulation's leaf (mcts.py:268-290 at recursion depth 0)
+    // the position is carried down the path (one `play` per level) instead of being read back from the parent's
+    // header when the leaf is reached: that read was a dependent memory round trip
+    Pos p;
+    {
         uint32_t rs[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) rs[k] = cp->root_state[k];
-        Pos p = unpack(rs);
+        p = unpack(rs);
+    }
+    if (root_idx < 0) {
+        // root never expanded: it is this simulation's leaf (mcts.py:268-290 at recursion depth 0)
         uint32_t am[3];
         int status;
         warp_legal_mask(p, lane, am, status);
@@ -281,7 +292,6 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
         if (idx < 0) idx = create_leaf(ts, tree, w, p, h, free_slot, am, lane, root_off, root_n);
         root_idx = idx;
     } else {
-        int cur = root_idx;
         uint32_t off = root_off, n = root_n;
         while (true) {
             EdgeBlock eb = edge_block(ts, tree, off, n);
@@ -381,19 +391,15 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
                 terminal += 1;
                 break;
             }
+            const int action = (int)(meta & 0xFFu);
             if (child != CHILD_UNRESOLVED) {
-                cur = (int)child;
+                p = play(p, action);
                 off = coff;
                 n = (meta >> 8) & 0xFFu;
                 continue;
             }
 
             // first traversal of this edge: successor position (mcts.py:319-320)
-            uint4 h0 = hdr[2ull * cur], h1 = hdr[2ull * cur + 1];
-            Pos p;
-            uint32_t pn, poff;
-            unpack_hdr(h0, h1, p, pn, poff);
-            const int action = (int)(meta & 0xFFu);
             Pos nx = play(p, action);
             uint32_t nam[3];
             int nst;
@@ -418,7 +424,7 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
                     eb.meta[best_j] = (uint32_t)action | (cn << 8);
                 }
                 transp += 1;
-                cur = idx;
+                p = nx;
                 off = co;
                 n = cn;
                 continue;
@@ -449,6 +455,9 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
         cp->leaf_node = w.leaf_node;
         cp->leaf_row = w.leaf_row;
         cp->leaf_value = w.leaf_value;
+        cp->leaf_off = w.leaf_off;
+        cp->leaf_n = w.leaf_n;
+        cp->leaf_am[0] = w.leaf_am[0]; cp->leaf_am[1] = w.leaf_am[1]; cp->leaf_am[2] = w.leaf_am[2];
         cp->path_len = (int)depth;
         cp->sims += 1;
         cp->sum_depth += depth;
@@ -489,14 +498,9 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
     int path_len = cp->path_len;
     double x;
     if (kind == LEAF_NN) {
-        int node = cp->leaf_node, row = cp->leaf_row;
-        const uint4 *hdr = ts.node_hdr + 2ull * ((size_t)tree * ts.capN + node);
-        Pos p;
-        uint32_t n, off;
-        unpack_hdr(hdr[0], hdr[1], p, n, off);
-        uint32_t am[3];
-        int status;
-        warp_legal_mask(p, lane, am, status);
+        const int row = cp->leaf_row;
+        const uint32_t n = cp->leaf_n, off = cp->leaf_off;
+        const uint32_t am[3] = {cp->leaf_am[0], cp->leaf_am[1], cp->leaf_am[2]};
         const float *pi = ts.eval_pi + 81 * (size_t)row;
         double m[3];
 #pragma unroll
@@ -540,6 +544,7 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
 
 __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
 {
+    griddep_launch(ts.pdl_trigger);
     griddep_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && ts.eval_count_next) *ts.eval_count_next = 0;
     const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -559,6 +564,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
 // expansion/backup, then walks down again while the path's nodes are still in cache.
 __global__ void __launch_bounds__(128, 7) k_backup_select(TreeStore ts, double cpuct)
 {
+    griddep_launch(ts.pdl_trigger);
     griddep_wait();
     // the other counter of the pair was last read by the evaluator kernels of the previous simulation, which have
     // completed; the next simulation's descent starts counting from zero without a memset node in the stream

@@ -47,6 +47,11 @@ struct TreeCtl {
     double leaf_value;       // value of a terminal leaf seen by its side to move (mcts.py:254-258)
     uint32_t root_off;       // edge block of the root
     uint32_t root_n;
+    // the leaf awaiting evaluation, as the descent left it: its edge block and legal moves (action order), so that the
+    // expansion needs neither the node header nor the rules again
+    uint32_t leaf_off, leaf_n;
+    uint32_t leaf_am[3];
+    uint32_t pad_;
     // counters
     unsigned long long sims, sum_depth, sum_legal, nn_leaves, sum_leaf_legal, terminal_leaves, transpositions;
 };
@@ -65,6 +70,7 @@ struct TreeStore {
     int *eval_count;
     int *eval_count_next;       // counter of the NEXT simulation, zeroed by this one's descent kernel (or null)
     int *error_flag;
+    int pdl_trigger;            // griddepcontrol.launch_dependents at kernel entry (common.cuh)
     int priors_masked;          // eval_pi is already masked + renormalised (TC_EVAL_NET_BF16_MASKED): store it as is
 };
 

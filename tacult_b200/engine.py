@@ -261,6 +261,16 @@ def rules_encode_obs(states):
     return out
 
 
+def rules_encode_history(states):
+    """8-frame (or any-frame) history planes, the C_in = 4 * frames input of BASELINE.json configs[4]:
+    states u32[n, frames, 8] (frame 0 = the current position, each in its own mover's canonical frame) ->
+    obs f32[n, 4 * frames, 9, 9], frame f in planes 4 f .. 4 f + 3.  The reference network has 4 planes and no history
+    (network.py:55); this is the new-engine variant, encoded by the same device kernel as a single frame."""
+    states = np.ascontiguousarray(states, dtype=np.uint32)
+    n, frames = states.shape[0], states.shape[1]
+    return rules_encode_obs(states.reshape(n * frames, 8)).reshape(n, 4 * frames, 9, 9)
+
+
 def rules_playouts(seed, first_game, n, max_plies=81):
     lib = _lib.load()
     res = (_lib.PlayoutResult * n)()

@@ -187,3 +187,34 @@ def test_search_in_production_mode_keeps_its_invariants():
     # float32 vs float64 renormalisation only moves priors in the last bits: the visit counts agree almost everywhere
     same = (counts[BF16] == counts[tb._lib.EVAL_NET_BF16_MASKED]).all(1).mean()
     assert same > 0.9, same
+
+
+@pytest.mark.parametrize("arch", [(32, 3, 256), (64, 2, 128), (256, 2, 256)])
+def test_history_variant_32_input_planes(arch):
+    """C_in = 32 (8 frames x 4 planes, BASELINE.json configs[4]): not in the reference (network.py:55 hard-codes 4), so
+    the check is against the same architecture in torch fp32 (tacult_b200/network.py:TrunkNet(in_planes=32)) —
+    1e-3 for the fp32 path, 2e-2 for bf16 — on history planes encoded on the device from real game trajectories."""
+    import torch
+    from tacult_b200.network import TrunkNet
+    torch.manual_seed(3)
+    net = TrunkNet(arch[0], arch[1], arch[2], dropout=0.0, in_planes=32).eval()
+    sd = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+    # trajectories: frame f = the position f plies ago (initial position repeated before the game started)
+    n, frames = 300, 8
+    hist = np.zeros((n, frames, 8), dtype=np.uint32)
+    for plies in range(frames + 20):
+        res = tb.rules_playouts(12, 0, n, max_plies=plies + 1)
+        cur = np.array([list(r.final_state) for r in res], dtype=np.uint32)
+        hist = np.concatenate([cur[:, None], hist[:, :-1]], axis=1)
+    obs = tb.rules_encode_history(hist)
+    assert obs.shape == (n, 32, 9, 9)
+    one = tb.rules_encode_obs(hist[:, 3])
+    assert np.array_equal(obs[:, 12:16], one)
+    with torch.no_grad():
+        rpi, rv = net(torch.from_numpy(obs))
+    eng = tb.Engine(n, 2)
+    eng.load_weights(sd)
+    pi, v = eng.forward(obs, F32)
+    assert np.abs(pi - rpi.numpy()).max() < 1e-3 and np.abs(v - rv.numpy().ravel()).max() < 1e-3
+    pi, v = eng.forward(obs, BF16)
+    assert np.abs(pi - rpi.numpy()).max() < TOL_BF16 and np.abs(v - rv.numpy().ravel()).max() < TOL_BF16
