@@ -686,10 +686,12 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
         eng.search(sims, CPUCT)
         counts = eng.root_counts()
         tau_one = (ply_no + 1) < TEMP_THRESHOLD
-        cum = np.cumsum(counts, axis=1, dtype=np.int64)
-        draw = (rng.random_sample(E) * cum[:, -1]).astype(np.int64)
-        sampled = (cum > draw[:, None]).argmax(1)               # a ~ counts / sum (coach.py:140)
-        acts = np.where(tau_one, sampled, counts.argmax(1))
+        acts = counts.argmax(1)                                     # tau = 0: arg-max (lowest index on ties)
+        rows = np.flatnonzero(tau_one)
+        if rows.size:                                               # tau = 1: a ~ counts / sum (coach.py:140)
+            cum = np.cumsum(counts[rows], axis=1, dtype=np.int64)
+            draw = (rng.random_sample(rows.size) * cum[:, -1]).astype(np.int64)
+            acts[rows] = (cum > draw[:, None]).argmax(1)
         nxt, st = tb.rules_step(states, acts.astype(np.int8))
         states[:] = nxt
         ply_no[:] += 1

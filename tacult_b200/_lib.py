@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libtacult_b200.so")
+# TACULT_B200_LIB: another build of the same library (A/B runs of kernel variants); default = the in-tree build
+LIB_PATH = os.environ.get("TACULT_B200_LIB") or os.path.join(HERE, "lib", "libtacult_b200.so")
 
 ABI_VERSION = 2
 TC_OK, TC_EINVAL, TC_ECUDA, TC_ECAPACITY, TC_ESTATE, TC_EILLEGAL = 0, -1, -2, -3, -4, -5

@@ -127,6 +127,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     // ---- prologue that depends on nothing the previous kernel wrote: it overlaps that kernel's tail (programmatic
     //      dependent launch, common.cuh) ----
     griddep_launch(P.pdl_trigger);
+    // optional marks of CTA 0 (TACULT_FUSED_TIMELINE): kernel entry, prologue done, dependency wait over, first planes
+    // encoded, every group done, exit — where a launch spends the time that is not layer work
+    long long *marks = (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? P.timeline + 8 * 32 : nullptr;
+    if (marks) marks[0] = clock64();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW_stem);
         tma_prefetch_desc(&tmW_conv);
@@ -141,7 +145,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
         reinterpret_cast<uint4 *>(Ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
 
     // ---- from here on the leaf count and the leaf positions written by the descent kernel are read ----
+    if (marks) marks[1] = clock64();
     griddep_wait();
+    if (marks) marks[2] = clock64();
     int count = P.batch;
     if (P.count_dev) count = min(count, *P.count_dev);
     // The live positions are dealt out evenly: CTA b owns positions [b * per, (b + 1) * per) and walks them in groups of
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
             fence_async_smem();
         }
         __syncthreads();
+        if (marks && group < 4) marks[3 + 2 * group] = clock64();
 
         // Layers are NOT separated by a block-wide barrier: tile t of layer l+1 only needs the activations of tiles
         // t-1, t, t+1 of layer l (taps reach 11 rows), so its UMMAs start as soon as those three epilogues have
@@ -364,10 +371,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        if (marks && group < 4) marks[4 + 2 * group] = clock64();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+    if (marks) { marks[11] = clock64(); marks[12] = n_my_groups; marks[13] = p_end - p_begin; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -425,7 +434,7 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
     P.pdl_trigger = pdl_trigger_enabled();
     static long long *timeline_dev = nullptr;
     if (getenv("TACULT_FUSED_TIMELINE")) {
-        if (!timeline_dev) cudaMalloc(&timeline_dev, 8 * 64 * sizeof(long long));
+        if (!timeline_dev) { cudaMalloc(&timeline_dev, 8 * 64 * sizeof(long long)); cudaMemset(timeline_dev, 0, 8 * 64 * sizeof(long long)); }
         P.timeline = timeline_dev;
     }
     const size_t smem = fused_smem_bytes(C, T);
@@ -448,6 +457,11 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
         for (int l = 0; l <= n_conv; ++l)
             fprintf(stderr, "[fused timeline] %2d: %7lld %7lld %7lld %7lld %7lld\n", l, h[8 * l] - h[0], h[8 * l + 1] - h[0],
                     h[8 * l + 2] - h[0], h[8 * l + 3] - h[0], h[8 * l + 4] - h[0]);
+        const long long *m = h + 8 * 32;
+        fprintf(stderr, "[fused marks] CTA 0, %lld positions in %lld groups; cycles since kernel entry: prologue done %lld | "
+                "dependency wait over %lld | group 0 planes %lld done %lld | group 1 planes %lld done %lld | exit %lld\n",
+                m[13], m[12], m[1] - m[0], m[2] - m[0], m[3] - m[0], m[4] - m[0], m[12] > 1 ? m[5] - m[0] : 0,
+                m[12] > 1 ? m[6] - m[0] : 0, m[11] - m[0]);
     }
     return TC_OK;
 }

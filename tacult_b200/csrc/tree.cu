@@ -96,13 +96,19 @@ __device__ int table_find(const TreeStore &ts, int tree, const Pos &p, uint64_t 
     return -1;
 }
 
+// TC_TRACK_POS=1: the descent carries the position down the path (one `play` per level) instead of reading the parent's
+// header back when it reaches the leaf.  Measured on B200: 0 = 35.8 us, 1 = 37.0 us per launch at 4096 trees (the extra
+// registers spill), so the header read stays.
+#ifndef TC_TRACK_POS
+#define TC_TRACK_POS 0
+#endif
+
 // per-warp view of the mutable part of TreeCtl, kept in registers during k_select
 struct Walk {
     uint32_t n_nodes, n_edges;
     int active, leaf_kind, leaf_node, leaf_row;
     double leaf_value;
     uint32_t nn_leaves, sum_leaf_legal;
-    uint32_t leaf_off, leaf_n, leaf_am[3];
 };
 
 // Creates a node for `p` (action mask am) and requests its evaluation.  Returns the node index, or -1 if a
@@ -147,9 +153,12 @@ __device__ int create_leaf(const TreeStore &ts, int tree, Walk &w, const Pos &p,
     w.leaf_kind = LEAF_NN;
     w.leaf_node = (int)idx;
     w.leaf_row = row;
-    w.leaf_off = off;
-    w.leaf_n = n;
-    w.leaf_am[0] = am[0]; w.leaf_am[1] = am[1]; w.leaf_am[2] = am[2];
+    if (lane == 0) {           // what the expansion needs, straight into the control block (not carried in registers)
+        TreeCtl *cp = ts.ctl + tree;
+        cp->leaf_off = off;
+        cp->leaf_n = n;
+        cp->leaf_am[0] = am[0]; cp->leaf_am[1] = am[1]; cp->leaf_am[2] = am[2];
+    }
     w.nn_leaves += 1;
     w.sum_leaf_legal += n;
     return (int)idx;
@@ -264,18 +273,14 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
     w.leaf_value = 0.0;
     w.nn_leaves = 0;
     w.sum_leaf_legal = 0;
-    w.leaf_off = w.leaf_n = 0;
-    w.leaf_am[0] = w.leaf_am[1] = w.leaf_am[2] = 0;
     int root_idx = cp->root_idx;
     uint32_t root_off = cp->root_off, root_n = cp->root_n;
     uint32_t depth = 0, sum_legal = 0, terminal = 0, transp = 0;
     uint2 *path = ts.path + (size_t)tree * MAX_DEPTH;
     const uint4 *hdr = ts.node_hdr + 2ull * (size_t)tree * ts.capN;
 
-    // the position is carried down the path (one `play` per level) instead of being read back from the parent's
-    // header when the leaf is reached: that read was a dependent memory round trip
     Pos p;
-    {
+    if (TC_TRACK_POS || root_idx < 0) {
         uint32_t rs[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) rs[k] = cp->root_state[k];
@@ -293,6 +298,9 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
         root_idx = idx;
     } else {
         uint32_t off = root_off, n = root_n;
+#if !TC_TRACK_POS
+        int cur = root_idx;
+#endif
         while (true) {
             EdgeBlock eb = edge_block(ts, tree, off, n);
             EdgeRegs e[3];
@@ -393,13 +401,23 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             }
             const int action = (int)(meta & 0xFFu);
             if (child != CHILD_UNRESOLVED) {
+#if TC_TRACK_POS
                 p = play(p, action);
+#else
+                cur = (int)child;
+#endif
                 off = coff;
                 n = (meta >> 8) & 0xFFu;
                 continue;
             }
 
             // first traversal of this edge: successor position (mcts.py:319-320)
+#if !TC_TRACK_POS
+            {
+                uint32_t pn, poff;
+                unpack_hdr(hdr[2ull * cur], hdr[2ull * cur + 1], p, pn, poff);
+            }
+#endif
             Pos nx = play(p, action);
             uint32_t nam[3];
             int nst;
@@ -424,7 +442,11 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
                     eb.meta[best_j] = (uint32_t)action | (cn << 8);
                 }
                 transp += 1;
+#if TC_TRACK_POS
                 p = nx;
+#else
+                cur = idx;
+#endif
                 off = co;
                 n = cn;
                 continue;
@@ -455,9 +477,6 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
         cp->leaf_node = w.leaf_node;
         cp->leaf_row = w.leaf_row;
         cp->leaf_value = w.leaf_value;
-        cp->leaf_off = w.leaf_off;
-        cp->leaf_n = w.leaf_n;
-        cp->leaf_am[0] = w.leaf_am[0]; cp->leaf_am[1] = w.leaf_am[1]; cp->leaf_am[2] = w.leaf_am[2];
         cp->path_len = (int)depth;
         cp->sims += 1;
         cp->sum_depth += depth;

@@ -89,9 +89,10 @@ class Engine:
         check(self.lib.tc_set_hash_evaluator(self.handle, int(salt) & (2 ** 64 - 1), int(pi_levels), int(v_levels)))
         self.set_evaluator(_lib.EVAL_HASH)
 
-    def load_weights(self, state_dict):
+    def load_weights(self, state_dict, plane_order=None):
+        """plane_order: see weights.state_dict_to_blob (checkpoints trained on another ordering of the input planes)."""
         from .weights import state_dict_to_blob
-        desc, blob = state_dict_to_blob(state_dict)
+        desc, blob = state_dict_to_blob(state_dict, plane_order)
         assert blob.size == self.lib.tc_weight_blob_floats(ctypes.byref(desc))
         check(self.lib.tc_load_weights(self.handle, ctypes.byref(desc), ptr(blob), blob.size))
         self.net_desc = desc

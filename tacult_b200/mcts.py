@@ -79,7 +79,7 @@ class VectorizedMCTS:
             self.engine.set_hash_evaluator(*hp)
             return
         module = getattr(nnet, "nnet", nnet)    # NNetWrapper.nnet (nn_wrapper.py:27) or a bare module
-        self.engine.load_weights(module.state_dict())
+        self.engine.load_weights(module.state_dict(), plane_order=_opt(args, "tc_plane_order", None))
         mode = str(_opt(args, "tc_evaluator", "f32")).lower()
         self.engine.set_evaluator({"bf16": _lib.EVAL_NET_BF16, "bf16_masked": _lib.EVAL_NET_BF16_MASKED}.get(mode, _lib.EVAL_NET_F32))
 

@@ -23,8 +23,24 @@ def _strip(state_dict):
     return out
 
 
-def state_dict_to_blob(state_dict):
-    sd = _strip(state_dict)
+ENGINE_PLANES = ("side-to-move stones", "opponent stones", "legal cells", "ones")
+
+
+def state_dict_to_blob(state_dict, plane_order=None):
+    """plane_order[i] = which ENGINE plane (ENGINE_PLANES) the network's input plane i was trained on.  The engine always
+    builds its four planes in ENGINE_PLANES order (the reference does not pin `get_obs()`), so a
+    checkpoint trained on another ordering is served by permuting conv_in's input channels here — the forward result is
+    the same as feeding the planes in the checkpoint's own order.  None = identity."""
+    sd = dict(_strip(state_dict))
+    if plane_order is not None:
+        order = [int(x) for x in plane_order]
+        w = _np(sd["conv_in.weight"])
+        if sorted(order) != list(range(w.shape[1])):
+            raise ValueError(f"plane_order must be a permutation of 0..{w.shape[1] - 1}, got {order}")
+        permuted = np.empty_like(w)
+        for net_plane, engine_plane in enumerate(order):
+            permuted[:, engine_plane] = w[:, net_plane]
+        sd["conv_in.weight"] = permuted
     conv_in = _np(sd["conv_in.weight"])
     channels, in_planes = conv_in.shape[0], conv_in.shape[1]
     blocks = 0

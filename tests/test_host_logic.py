@@ -66,3 +66,27 @@ def test_dihedral_images_match_reference_symmetries():
         for k, (b, p) in enumerate(syms):
             assert np.array_equal(np.asarray(b.get_obs()).reshape(4, 9, 9), obs_imgs[k])
             assert np.array_equal(p, pi_imgs[k].reshape(81))
+
+
+def test_plane_order_permutes_conv_in_channels():
+    sd = resnet_oracle.make_state_dict(2, 16, 1, 64)
+    _, base = state_dict_to_blob(sd)
+    _, same = state_dict_to_blob(sd, plane_order=(0, 1, 2, 3))
+    assert np.array_equal(base, same)
+    _, swapped = state_dict_to_blob(sd, plane_order=(1, 0, 2, 3))       # the net's plane 0 is the engine's plane 1
+    w = sd["conv_in.weight"]
+    want = w.copy()
+    want[:, 1], want[:, 0] = w[:, 0], w[:, 1]
+    assert np.array_equal(swapped[:w.size], want.ravel()) and np.array_equal(swapped[w.size:], base[w.size:])
+    # feeding permuted planes to the original net == feeding engine-order planes to the permuted net
+    x = (np.random.RandomState(0).random_sample((5, 4, 9, 9)) < 0.4).astype(np.float32)
+    sd2 = dict(sd)
+    sd2["conv_in.weight"] = want
+    a = resnet_oracle.forward(sd, x[:, [1, 0, 2, 3]])
+    b = resnet_oracle.forward(sd2, x)
+    assert np.allclose(a[0].numpy(), b[0].numpy(), atol=1e-6) and np.allclose(a[1].numpy(), b[1].numpy(), atol=1e-6)
+    try:
+        state_dict_to_blob(sd, plane_order=(0, 0, 1, 2))
+        raise AssertionError("non-permutation accepted")
+    except ValueError:
+        pass
