@@ -363,6 +363,10 @@ def run_b200(a):
     # ---- BASELINE.json configs[4]: the deep 256ch x 20 trunk, where the conv GEMMs are tensor-bound -------------
     if not a.skip_extras:
         extras["deep_net"] = deep_net_leg(tb, torch, stream, local, reduce_scalar, dist, world)
+        # ---- BASELINE.json configs[1]: arena of two random-init nets, 1024 games x 2 sims/move (small-batch latency) ----
+        if rank == 0:
+            extras["c2_arena"] = arena_leg(tb, local)
+        barrier()
 
     # ---- N>1, BASELINE.json configs[3]: 4096 trees x 800 sims per rank, every game to completion, then the iteration's
     #      one exchange step — records drained on the device and all-gathered over NCCL — inside the measured span -----
@@ -543,6 +547,31 @@ def deep_net_leg(tb, torch, stream, local, reduce_scalar, dist, world):
             "frac_of_burst_bf16_peak": tf / peaks["bf16_tflops"]}
 
 
+def arena_leg(tb, local, games=1024, envs=512, sims=2):
+    """`VectorizedArena.playGames` semantics (base/arena.py:216-305) on packed boards, host buffers through the C ABI."""
+    from tacult_b200.arena import PackedArena
+    from tacult_b200.weights import random_state_dict
+    engines = []
+    for seed in (0, 1):
+        e = tb.Engine(envs, 8 * (sims * 82 + 64), device=local)
+        e.load_weights(random_state_dict(seed, **NET))
+        e.set_evaluator(tb._lib.EVAL_NET_BF16)
+        engines.append(e)
+    PackedArena(engines[0], engines[1], sims, CPUCT, tie_break="lowest").play_games(2 * envs)       # warm-up pass each way
+    arena = PackedArena(engines[0], engines[1], sims, CPUCT, tie_break="lowest")
+    t0 = time.perf_counter()
+    one, two, draws = arena.play_games(games)
+    dt = time.perf_counter() - t0
+    ply = np.array(arena.ply_seconds) * 1e3
+    for e in engines:
+        e.close()
+    return {"workload": f"arena {games} games x {sims} sims/move, {envs} boards per pass, two trainer-default nets, bf16",
+            "games_per_sec": games / dt, "sims_per_sec": arena.sims / dt, "seconds": dt, "plies": int(len(ply)),
+            "ply_ms_p50": float(np.percentile(ply, 50)), "ply_ms_p99": float(np.percentile(ply, 99)),
+            "result": [int(one), int(two), int(draws)],
+            "path": "host buffers per ply: tc_set_roots_packed -> tc_search -> tc_root_counts -> arg-max -> tc_rules_step"}
+
+
 def c4_leg(a, tb, torch, stream, local, rank, world, evaluator, barrier, reduce_scalar, dist):
     from tacult_b200.distributed import DeviceReplay, DeviceTrajectoryExchange
     from tacult_b200.weights import random_state_dict
@@ -554,7 +583,7 @@ def c4_leg(a, tb, torch, stream, local, rank, world, evaluator, barrier, reduce_
     xchg = DeviceTrajectoryExchange(eng, torch.device("cuda", local))
     eng.selfplay_begin(sims, CPUCT, TEMP_THRESHOLD, seed=5000 + rank, auto_reset=False)
     eng.selfplay_sync()
-    dist.all_reduce(torch.zeros(1, device="cuda"))            # NCCL communicator up before the clock starts
+    xchg.warm_up()                                             # receive buffer + NCCL channels up before the clock starts
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     barrier()
     torch.cuda.synchronize()

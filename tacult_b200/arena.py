@@ -41,10 +41,13 @@ class PackedArena:
         counts = engine.root_counts().astype(np.int64)
         if self.tie_break == "lowest":
             return counts.argmax(axis=1)
-        actions = np.empty(self.num_envs, dtype=np.int64)
-        for i in range(self.num_envs):                       # same draws as getActionProbs(temps=0) + argmax
-            best = np.flatnonzero(counts[i] == counts[i].max())
-            actions[i] = np.random.choice(best)
+        # same draws as getActionProbs(temps=0) + argmax: `np.random.choice(best)` is one `randint(0, len(best))`, which
+        # draws nothing for a single candidate, so only tied rows touch the generator — in env order
+        is_top = counts == counts.max(axis=1, keepdims=True)
+        actions = is_top.argmax(axis=1)
+        for i in np.flatnonzero(is_top.sum(axis=1) > 1):
+            best = np.flatnonzero(is_top[i])
+            actions[i] = best[np.random.randint(0, len(best))]
         return actions
 
     def _one_pass(self, first, second):

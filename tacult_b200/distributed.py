@@ -68,7 +68,22 @@ class DeviceTrajectoryExchange:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self._counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
         self._mine = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self._recv = None
+        self._recv = self._compact = None
+
+    def warm_up(self, records_per_rank=None):
+        """Allocates the receive buffer for `records_per_rank` records from every rank (default: one game of 81 plies per
+        env) and runs both collectives once, so that the first real exchange of an iteration pays neither cudaMalloc nor
+        NCCL's lazy channel set-up."""
+        n = int(records_per_rank or min(self.capacity, self.engine.num_envs * 81))
+        if self.world == 1:
+            return
+        need = self.world * n * RECORD_BYTES
+        if self._recv is None or self._recv.numel() < need:
+            self._recv = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._compact = torch.empty(need, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(self._counts, self._mine, group=self.group)
+        dist.all_gather_into_tensor(self._recv[:need], self.send[: n * RECORD_BYTES], group=self.group)
+        torch.cuda.synchronize(self.device)
 
     def drain(self):
         """This rank's finished-game records into the send buffer; returns the count."""
@@ -89,12 +104,19 @@ class DeviceTrajectoryExchange:
         need = self.world * n_max * RECORD_BYTES
         if self._recv is None or self._recv.numel() < need:
             self._recv = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._compact = torch.empty(need, dtype=torch.uint8, device=self.device)
         recv = self._recv[:need]
         dist.all_gather_into_tensor(recv, self.send[: n_max * RECORD_BYTES], group=self.group)
         rows = recv.view(self.world, n_max, RECORD_BYTES)
         if all(c == n_max for c in counts):
             return rows.view(self.world * n_max, RECORD_BYTES), counts
-        return torch.cat([rows[r, : counts[r]] for r in range(self.world)], dim=0), counts
+        # ragged: close the gaps with device-to-device copies into the persistent compact buffer (no allocation)
+        out = self._compact[: sum(counts) * RECORD_BYTES].view(sum(counts), RECORD_BYTES)
+        at = 0
+        for r in range(self.world):
+            out[at:at + counts[r]].copy_(rows[r, : counts[r]])
+            at += counts[r]
+        return out, counts
 
 
 class DeviceReplay:
