@@ -3,20 +3,21 @@
 # commands under ncu.  Outputs land in gpurun_out/; tools/ncu_summary.py turns them into profiles/*.json here.
 set -u
 mkdir -p gpurun_out
-TAG=${1:-r01_final}
+TAG=${1:-r02_final}
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
-timeout 600 python bench.py > gpurun_out/bench_$TAG.log 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; echo "reference arm rc=$?"
+timeout 900 python bench.py > gpurun_out/bench_$TAG.log 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; echo "reference arm rc=$?"
 timeout 300 python tools/eval_sweep.py --net deep --batches 256,1024,4096,16384,65536 > gpurun_out/sweep_deep_$TAG.jsonl 2>&1; echo "deep sweep rc=$?"
+timeout 300 python tools/eval_sweep.py --net deep --in-planes 32 --batches 256,1024,4096,16384,65536 > gpurun_out/sweep_deep_in32_$TAG.jsonl 2>&1; echo "deep C_in=32 sweep rc=$?"
 timeout 300 python tools/eval_sweep.py --net trainer --batches 256,1024,4096,16384,65536 > gpurun_out/sweep_trainer_$TAG.jsonl 2>&1; echo "trainer sweep rc=$?"
-timeout 200 python tools/arena_bench.py > gpurun_out/arena_$TAG.json 2>&1; echo "arena rc=$?"
+SHORT="python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --skip-extras --profile-plies 0"
 # launch list of a short bench run (per-launch durations are cold-cache and serialised: shares, not absolutes)
-timeout 200 python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --skip-extras --profile-plies 0 > gpurun_out/plain_short.log 2>&1; echo "short plain rc=$?"
+timeout 200 $SHORT > gpurun_out/plain_short_$TAG.log 2>&1; echo "short plain rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --skip-extras --profile-plies 0 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launch list rc=$?"
+    $SHORT > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launch list rc=$?"
 # one full capture per hot kernel (skip the warm-up launches)
-for K in k_trunk_fused k_backup_select k_fc1_splitk k_gemm_tc; do
+for K in k_trunk_fused k_backup_select k_fc1_heads; do
   timeout 900 ncu --set full --import-source on --clock-control none -k regex:$K -s 300 -c 1 -f -o gpurun_out/prof_${K}_$TAG \
-      python bench.py --steps 1 --warmup 1 --stagger-plies 20 --skip-e2e --skip-cpu-baseline --skip-extras --profile-plies 0 > gpurun_out/ncu_$K.log 2>&1; echo "ncu $K rc=$?"
+      $SHORT > gpurun_out/ncu_${K}_$TAG.log 2>&1; echo "ncu $K rc=$?"
 done
 tail -1 gpurun_out/bench_$TAG.log | cut -c1-300
