@@ -58,3 +58,24 @@ def test_packed_arena_lowest_index_mode_is_deterministic():
         e2.set_hash_evaluator(4)
         results.append(PackedArena(e1, e2, num_sims=8, cpuct=2.4, tie_break="lowest").play_games(64))
     assert results[0] == results[1] and sum(results[0]) == 64
+
+
+def test_reference_coach_runs_on_product_gamestate_and_gpu_search(golden):
+    """INTEGRATION.md end to end: the unmodified reference `Coach.generateTrainExamples` + `UtacGame` with
+    `utac_gym.core.GameState` served by tacult_b200.GameState and `MCTS` replaced by tacult_b200.VectorizedMCTS gives
+    the training examples the live reference produced (callers.npz), bit for bit.  Needs the staged reference
+    modules (oracle/_ref, written by __graft_entry__.build() in the build container)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if not (os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "src", "tacult", "base", "coach.py"))
+            or os.path.isfile("/root/reference/src/tacult/base/coach.py")):
+        pytest.skip("reference modules not staged (oracle/_ref)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_reference_coach.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("EXAMPLES")][-1].split()
+    g = golden("callers.npz")
+    assert int(line[1]) == int(g["coach_examples"])
+    assert line[2] == bytes(g["coach_sha256"]).hex()
