@@ -584,7 +584,7 @@ def c4_leg(a, tb, torch, stream, local, rank, world, evaluator, barrier, reduce_
     eng.selfplay_begin(sims, CPUCT, TEMP_THRESHOLD, seed=5000 + rank, auto_reset=False)
     eng.selfplay_sync()
     xchg.warm_up()                                             # receive buffer + NCCL channels up before the clock starts
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     barrier()
     torch.cuda.synchronize()
     ev[0].record(stream)
@@ -595,16 +595,22 @@ def c4_leg(a, tb, torch, stream, local, rank, world, evaluator, barrier, reduce_
         if plies >= 17 and eng.selfplay_stats()["games_finished"] >= E:
             break
     ev[1].record(stream)
-    records, counts = xchg.gather()                            # drain on the device + counts + padded all-gather
-    replay = DeviceReplay(eng, records)
+    # the ranks finish their last game at different times: align them, so that the exchange is timed on its own and not
+    # as "waiting for the slowest rank" (the play phase is already the max over ranks)
+    torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
     ev[2].record(stream)
+    records, counts = xchg.gather()                            # drain on the device + counts + all-gather + compaction
+    replay = DeviceReplay(eng, records)
+    ev[3].record(stream)
     torch.cuda.synchronize()
     barrier()
     eng.selfplay_sync()
     st = eng.selfplay_stats()
     play_ms = reduce_scalar(ev[0].elapsed_time(ev[1]), dist.ReduceOp.MAX)
-    all_ms = reduce_scalar(ev[0].elapsed_time(ev[2]), dist.ReduceOp.MAX)
-    x_ms = reduce_scalar(ev[1].elapsed_time(ev[2]), dist.ReduceOp.MAX)
+    x_ms = reduce_scalar(ev[2].elapsed_time(ev[3]), dist.ReduceOp.MAX)
+    all_ms = play_ms + x_ms
     sims_done = reduce_scalar(float(st["sims"]), dist.ReduceOp.SUM)
     n_total = int(sum(counts))
     # a learner-side use of the gathered records, still on the device: one batch of examples (8 symmetries on the fly)
@@ -612,7 +618,7 @@ def c4_leg(a, tb, torch, stream, local, rank, world, evaluator, barrier, reduce_
     obs, pi, z = replay.examples(idx)
     ok = bool(torch.isfinite(obs).all() and torch.isfinite(pi).all() and (pi.sum(1) - 1).abs().max() < 1e-3)
     gathered = {"records_local": int(counts[rank]), "records_all_ranks": n_total, "ms": x_ms, "bytes_per_record": 216,
-                "effective_gbps": world * max(counts) * 216 / (x_ms * 1e-3) / 1e9 if x_ms > 0 else None,
+                "effective_gbps": n_total * 216 / (x_ms * 1e-3) / 1e9 if x_ms > 0 else None,
                 "path": "tc_selfplay_drain_dev -> persistent CUDA send buffer -> all_gather_into_tensor (NCCL) -> "
                         "device record tensor -> tc_examples_from_records_dev", "examples_ok": ok}
     eng.close()

@@ -106,6 +106,36 @@ class Learner:
             history.append((tot_pi / steps_per_epoch, tot_v / steps_per_epoch))
         return history
 
+    def train_from_replay(self, replay, epochs, steps_per_epoch, batch_size, shuffle=True, seed=0):
+        """The same epoch loop fed from a `distributed.DeviceReplay` (trajectory records resident in HBM): every step
+        draws the global batch of example ids (record x 8 + symmetry image) from the shared permutation, takes this
+        rank's rows and lets `tc_examples_from_records_dev` build exactly those (obs, pi, z) on the device — the
+        eight-fold augmented training set (coach.py:136-138) is never materialised."""
+        n = replay.n_examples
+        gen = torch.Generator().manual_seed(int(seed))          # same permutation on every rank
+        order, cursor = None, 0
+        history = []
+        self.net.train()
+        for _ in range(int(epochs)):
+            tot_pi = tot_v = 0.0
+            for _ in range(int(steps_per_epoch)):
+                if order is None or cursor >= n:
+                    order = torch.randperm(n, generator=gen) if shuffle else torch.arange(n)
+                    cursor = 0
+                idx = order[cursor:cursor + batch_size]
+                cursor += batch_size
+                if len(idx) < 2 * self.world and n >= 2 * self.world:
+                    short = len(idx)
+                    order = torch.randperm(n, generator=gen) if shuffle else torch.arange(n)
+                    cursor = min(n, batch_size - short)
+                    idx = torch.cat([idx, order[:cursor]])
+                obs, pi, z = replay.examples(idx[self.rank::self.world])
+                a, b = self.training_step(obs, pi, z, global_batch=len(idx))
+                tot_pi += a
+                tot_v += b
+            history.append((tot_pi / steps_per_epoch, tot_v / steps_per_epoch))
+        return history
+
     # -- weights out / in --------------------------------------------------------------------------
     def state_dict_numpy(self):
         return {k: v.detach().cpu().numpy() for k, v in self.net.state_dict().items()}

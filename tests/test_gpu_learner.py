@@ -44,3 +44,38 @@ def test_selfplay_train_publish_round_trip():
     # and the engine keeps playing with the new weights
     records2, stats2 = driver.play_records(seed=3)
     assert stats2["games_finished"] >= 64 and len(records2) > 0
+
+
+def test_training_from_device_replay_equals_training_from_host_arrays():
+    """Same seeds, same batches: the learner fed by `DeviceReplay` (records in HBM, examples built per step by
+    tc_examples_from_records_dev) ends with the very weights of the learner fed by the materialised host arrays."""
+    from tacult_b200.distributed import DeviceReplay, DeviceTrajectoryExchange
+    args = Args(numEnvs=48, numMCTSSims=6, cpuct=2.4, tempThreshold=8, tc_evaluator="f32")
+    torch.manual_seed(1)
+    net = TrunkNet(16, 1, 64, dropout=0.0)
+    driver = SelfPlayDriver(net, args)
+    eng = driver.engine
+    eng.selfplay_begin(6, 2.4, 8, seed=4, auto_reset=False)
+    eng.selfplay_step(81)
+    eng.selfplay_sync()
+    records, counts = DeviceTrajectoryExchange(eng, "cuda:0").gather()
+    replay = DeviceReplay(eng, records)
+    host = records.cpu().numpy().reshape(-1).view(tb._lib.EXAMPLE_DTYPE)
+    obs, pi, z = records_to_arrays(host, augment=True)
+    assert replay.n_examples == len(z) > 1000
+    # an id outside the record array gives a zero example, never a wild read
+    bad = torch.tensor([0, replay.n_examples + 5, -3], dtype=torch.int32, device="cuda")
+    bo, bp, bz = replay.examples(bad)
+    assert torch.equal(bo[0].cpu(), torch.from_numpy(obs[0])) and float(bo[1:].abs().sum() + bp[1:].abs().sum() + bz[1:].abs().sum()) == 0.0
+    results = []
+    for source in ("host", "device"):
+        torch.manual_seed(2)
+        learner = Learner(TrunkNet(16, 1, 64, dropout=0.0), lr=1e-3, device="cuda:0")
+        if source == "host":
+            hist = learner.train(obs, pi, z, epochs=1, steps_per_epoch=6, batch_size=512, seed=9)
+        else:
+            hist = learner.train_from_replay(replay, epochs=1, steps_per_epoch=6, batch_size=512, seed=9)
+        results.append((hist, {k: v.detach().cpu().clone() for k, v in learner.net.state_dict().items()}))
+    assert results[0][0] == results[1][0]
+    for k in results[0][1]:
+        assert torch.equal(results[0][1][k], results[1][1][k]), k
