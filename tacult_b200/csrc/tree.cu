@@ -102,6 +102,11 @@ __device__ int table_find(const TreeStore &ts, int tree, const Pos &p, uint64_t 
 #ifndef TC_TRACK_POS
 #define TC_TRACK_POS 0
 #endif
+// TC_PUCT_PREFILTER=1: decide the PUCT arg-max from float32 intervals when they separate the candidates, and only
+// fall back to the float64 evaluation on (near) ties; see select_tree.
+#ifndef TC_PUCT_PREFILTER
+#define TC_PUCT_PREFILTER 1
+#endif
 
 // per-warp view of the mutable part of TreeCtl, kept in registers during k_select
 struct Walk {
@@ -332,46 +337,90 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             }
             nsum = __reduce_add_sync(FULL, nsum);                                          // Ns[s]
 
-            // PUCT over the legal edges (mcts.py:301-316)
-            const double sq_visited = nsum ? __dsqrt_rn((double)nsum) : 0.0;      // only used by edges with N > 0
-            const double sq_fresh = __dsqrt_rn(__dadd_rn((double)nsum, 1e-8));
-            double best_u = -INFINITY;
+            // PUCT over the legal edges (mcts.py:301-316).
             int best_j = 1 << 20;
-            if ((uint32_t)lane < n) {
-                double cpp = __dmul_rn(cpuct, e[0].P);
-                best_u = e[0].N ? __dadd_rn(e[0].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[0].N)))
-                                : __dmul_rn(cpp, sq_fresh);
-                best_j = lane;
-                if (!(best_u > -INFINITY)) { best_u = -INFINITY; best_j = 1 << 20; }   // NaN / -inf is never selected (mcts.py:314)
-            }
-            if (n > 32) {
-#pragma unroll
-                for (int q = 1; q < 3; ++q) {
-                    const uint32_t j = (uint32_t)lane + 32u * q;
-                    if (j < n) {
-                        double cpp = __dmul_rn(cpuct, e[q].P);
-                        double u = e[q].N ? __dadd_rn(e[q].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[q].N)))
-                                          : __dmul_rn(cpp, sq_fresh);
-                        if (u > best_u) { best_u = u; best_j = (int)j; }   // ascending j: first maximum wins
+            bool decided = false;
+#if TC_PUCT_PREFILTER
+            // The arg-max only needs the float64 values when two candidates are close.  A float32 evaluation of the same
+            // formula is within 1e-6 * (|Q| + |U|) of the exact value (conversions, approximate sqrt and division, one
+            // rounding per operation); with a ten-fold margin, every edge gets an interval [u - eps, u + eps] that contains
+            // its exact score.  If only ONE edge's upper end reaches the best lower end, that edge is the unique exact
+            // maximum — no tie can exist, so no tie-break is needed — and the ~70 float64 instructions per level (two
+            // software square roots and a division, the kernel's issue-slot hogs) are skipped.  Otherwise (exact ties of
+            // equal priors, near ties, nodes wider than a warp) the exact path below decides, as before.
+            if (n <= 32u) {
+                const bool valid = (uint32_t)lane < n;
+                const float nsf = (float)nsum;                                   // exact below 2^24 visits
+                float u = 0.f, mag = 0.f;
+                if (valid) {
+                    const float cpf = (float)cpuct * (float)e[0].P;
+                    if (e[0].N) {
+                        const float qf = (float)e[0].Q;
+                        const float uf = __fdividef(cpf * __fsqrt_rn(nsf), (float)(1u + e[0].N));
+                        u = qf + uf;
+                        mag = fabsf(qf) + fabsf(uf);
+                    } else {
+                        u = cpf * __fsqrt_rn(nsf + 1e-8f);
+                        mag = fabsf(u);
                     }
                 }
-            }
-            // Warp arg-max in three REDUX steps instead of a 5-round shuffle butterfly: doubles are mapped to
-            // order-preserving unsigned keys (-0.0 folded into +0.0 first, so equal values give equal keys exactly
-            // as the reference's strict '>' sees them); max of the high words, max of the low words among the
-            // lanes that hold that high word, then the lowest edge index among the lanes that hold the maximum
-            // (edges are in action order: "lowest action index wins ties", mcts.py:314).
-            {
-                unsigned long long key = 0ull;                 // lanes without a candidate can never win
-                if (best_j < (1 << 20)) {
-                    long long bits = __double_as_longlong(__dadd_rn(best_u, 0.0));
-                    key = (unsigned long long)bits ^ (bits < 0 ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+                const float eps = 1e-5f * mag + 1e-30f;
+                auto okey = [](float x) {                                        // order-preserving float -> uint32
+                    const uint32_t bits = __float_as_uint(x);
+                    return bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+                };
+                const bool finite = valid && fabsf(u) < 1e30f;                   // also false for NaN
+                const uint32_t klo = finite ? okey(u - eps) : 0u;
+                const uint32_t best_lo = __reduce_max_sync(FULL, klo);
+                const unsigned any_bad = __ballot_sync(FULL, valid && !finite);
+                const unsigned cand = __ballot_sync(FULL, finite && okey(u + eps) >= best_lo);
+                if (!any_bad && __popc(cand) == 1) {
+                    best_j = __ffs(cand) - 1;
+                    decided = true;
                 }
-                const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-                const uint32_t mhi = __reduce_max_sync(FULL, hi);
-                const uint32_t mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
-                const bool top = best_j < (1 << 20) && hi == mhi && lo == mlo;
-                best_j = (int)__reduce_min_sync(FULL, top ? (uint32_t)best_j : (uint32_t)(1 << 20));
+            }
+#endif
+            if (!decided) {
+                const double sq_visited = nsum ? __dsqrt_rn((double)nsum) : 0.0;      // only used by edges with N > 0
+                const double sq_fresh = __dsqrt_rn(__dadd_rn((double)nsum, 1e-8));
+                double best_u = -INFINITY;
+                best_j = 1 << 20;
+                if ((uint32_t)lane < n) {
+                    double cpp = __dmul_rn(cpuct, e[0].P);
+                    best_u = e[0].N ? __dadd_rn(e[0].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[0].N)))
+                                    : __dmul_rn(cpp, sq_fresh);
+                    best_j = lane;
+                    if (!(best_u > -INFINITY)) { best_u = -INFINITY; best_j = 1 << 20; }   // NaN / -inf is never selected (mcts.py:314)
+                }
+                if (n > 32) {
+    #pragma unroll
+                    for (int q = 1; q < 3; ++q) {
+                        const uint32_t j = (uint32_t)lane + 32u * q;
+                        if (j < n) {
+                            double cpp = __dmul_rn(cpuct, e[q].P);
+                            double u = e[q].N ? __dadd_rn(e[q].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[q].N)))
+                                              : __dmul_rn(cpp, sq_fresh);
+                            if (u > best_u) { best_u = u; best_j = (int)j; }   // ascending j: first maximum wins
+                        }
+                    }
+                }
+                // Warp arg-max in three REDUX steps instead of a 5-round shuffle butterfly: doubles are mapped to
+                // order-preserving unsigned keys (-0.0 folded into +0.0 first, so equal values give equal keys exactly
+                // as the reference's strict '>' sees them); max of the high words, max of the low words among the
+                // lanes that hold that high word, then the lowest edge index among the lanes that hold the maximum
+                // (edges are in action order: "lowest action index wins ties", mcts.py:314).
+                {
+                    unsigned long long key = 0ull;                 // lanes without a candidate can never win
+                    if (best_j < (1 << 20)) {
+                        long long bits = __double_as_longlong(__dadd_rn(best_u, 0.0));
+                        key = (unsigned long long)bits ^ (bits < 0 ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+                    }
+                    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+                    const uint32_t mhi = __reduce_max_sync(FULL, hi);
+                    const uint32_t mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+                    const bool top = best_j < (1 << 20) && hi == mhi && lo == mlo;
+                    best_j = (int)__reduce_min_sync(FULL, top ? (uint32_t)best_j : (uint32_t)(1 << 20));
+                }
             }
             sum_legal += n;
             if (best_j >= (1 << 20)) {       // cannot happen for a live position; park the tree loudly
