@@ -350,17 +350,21 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             // equal priors, near ties, nodes wider than a warp) the exact path below decides, as before.
             if (n <= 32u) {
                 const bool valid = (uint32_t)lane < n;
-                const float nsf = (float)nsum;                                   // exact below 2^24 visits
+                // sqrt(Ns) for visited edges; sqrt(Ns + 1e-8) for fresh ones is the same float32 once Ns >= 1 (1e-8 is below
+                // half an ulp) and 1e-4 at Ns = 0; sqrt.approx is within 2^-23
+                float s0;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(s0) : "f"((float)nsum));    // (float)nsum is exact below 2^24 visits
+                const float s_fresh = nsum ? s0 : 1e-4f;
                 float u = 0.f, mag = 0.f;
                 if (valid) {
                     const float cpf = (float)cpuct * (float)e[0].P;
                     if (e[0].N) {
                         const float qf = (float)e[0].Q;
-                        const float uf = __fdividef(cpf * __fsqrt_rn(nsf), (float)(1u + e[0].N));
+                        const float uf = __fdividef(cpf * s0, (float)(1u + e[0].N));
                         u = qf + uf;
                         mag = fabsf(qf) + fabsf(uf);
                     } else {
-                        u = cpf * __fsqrt_rn(nsf + 1e-8f);
+                        u = cpf * s_fresh;
                         mag = fabsf(u);
                     }
                 }
