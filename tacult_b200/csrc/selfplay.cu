@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) k_selfplay_move(TreeStore ts, SelfPlaySto
         lg[q] = (a < 81) && action_bit(lw, a);
         am[q] = __ballot_sync(FULL, lg[q]);
     }
-    const uint32_t *edgeN = edge_block(ts, env, off, n).N;
+    const Edge *blk = tree_edges(ts, env) + off;
     uint32_t cnt[3];
     uint32_t total = 0, maxc = 0;
 #pragma unroll
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) k_selfplay_move(TreeStore ts, SelfPlaySto
         cnt[q] = 0;
         if (lg[q]) {
             int j = __popc(am[q] & ((1u << lane) - 1u)) + (q >= 1 ? __popc(am[0]) : 0) + (q >= 2 ? __popc(am[1]) : 0);
-            cnt[q] = edgeN[j];
+            cnt[q] = blk[j].N;
         }
         total += cnt[q];
         maxc = max(maxc, cnt[q]);

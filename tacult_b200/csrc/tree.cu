@@ -136,15 +136,14 @@ __device__ int create_leaf(const TreeStore &ts, int tree, Walk &w, const Pos &p,
         ts.node_hdr[2 * g + 1] = make_uint4(p.occ[1], p.occ[2], p.last | (n << 8), off);
         ts.hash[(size_t)tree * ts.hashSize + free_slot] = (((uint32_t)(h >> 40) & 0xFFFu) << 20) | (idx + 1u);
     }
-    EdgeBlock eb = edge_block(ts, tree, off, n);
+    Edge *blk = tree_edges(ts, tree) + off;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
+        if (am[q] == 0u) continue;                     // warp-uniform: most leaves have moves in one or two thirds only
         if ((am[q] >> lane) & 1u) {
-            int j = edge_index(am, q, lane);
-            eb.N[j] = 0u;
-            eb.child[j] = CHILD_UNRESOLVED;
-            eb.coff[j] = 0u;
-            eb.meta[j] = (uint32_t)(lane + 32 * q);
+            uint4 *rec = reinterpret_cast<uint4 *>(blk + edge_index(am, q, lane));
+            rec[0] = edge_pack(0.0, 0u, CHILD_UNRESOLVED);                       // Q, N, child
+            rec[1] = edge_pack(0.0, 0u, (uint32_t)(lane + 32 * q));              // P (set by the expansion), coff, meta
         }
     }
     int row = 0;
@@ -253,10 +252,68 @@ __global__ void k_set_roots(TreeStore ts, const uint32_t *__restrict__ states, c
     }
 }
 
-struct EdgeRegs {     // one edge as held by its lane during selection
-    double P, Q;
-    uint32_t N, child, coff, meta;
-};
+// Order-preserving map of a double to an unsigned key (-0.0 folded into +0.0 first, so equal values give equal keys
+// exactly as the reference's strict '>' sees them).
+__device__ __forceinline__ unsigned long long double_key(double u)
+{
+    long long bits = __double_as_longlong(__dadd_rn(u, 0.0));
+    return (unsigned long long)bits ^ (bits < 0 ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+}
+
+// Warp arg-max in three REDUX steps instead of a 5-round shuffle butterfly: max of the high words, max of the low words
+// among the lanes that hold that high word, then the lowest edge index among the lanes that hold the maximum (edges are in
+// action order: "lowest action index wins ties", mcts.py:314).  Lanes without a candidate pass j = 1 << 20.
+__device__ __forceinline__ int warp_argmax(double best_u, int best_j)
+{
+    unsigned long long key = 0ull;                 // lanes without a candidate can never win
+    if (best_j < (1 << 20)) key = double_key(best_u);
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mhi = __reduce_max_sync(FULL, hi);
+    const uint32_t mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+    const bool top = best_j < (1 << 20) && hi == mhi && lo == mlo;
+    return (int)__reduce_min_sync(FULL, top ? (uint32_t)best_j : (uint32_t)(1 << 20));
+}
+
+// PUCT score of one edge in float64, operation by operation as mcts.py:309-312 (no FMA contraction)
+__device__ __forceinline__ double puct_exact(double cpuct, double P, double Q, uint32_t N, double sq_visited, double sq_fresh)
+{
+    const double cpp = __dmul_rn(cpuct, P);
+    return N ? __dadd_rn(Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + N))) : __dmul_rn(cpp, sq_fresh);
+}
+
+// Selection at a node wider than a warp (free moves: up to 81 edges), three edges per lane, float64 throughout.
+__device__ __noinline__ int select_wide(const Edge *blk, uint32_t n, int lane, double cpuct)
+{
+    double P[3], Q[3];
+    uint32_t N[3], nsum = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const uint32_t j = (uint32_t)lane + 32u * q;
+        N[q] = 0;
+        P[q] = Q[q] = 0.0;
+        if (j < n) {
+            const uint4 st = edge_load_stats(blk + j), lk = edge_load_link(blk + j);
+            Q[q] = u2d(st.x, st.y);
+            N[q] = st.z;
+            P[q] = u2d(lk.x, lk.y);
+            nsum += N[q];
+        }
+    }
+    nsum = __reduce_add_sync(FULL, nsum);
+    const double sq_visited = nsum ? __dsqrt_rn((double)nsum) : 0.0;
+    const double sq_fresh = __dsqrt_rn(__dadd_rn((double)nsum, 1e-8));
+    double best_u = -INFINITY;
+    int best_j = 1 << 20;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const uint32_t j = (uint32_t)lane + 32u * q;
+        if (j < n) {
+            const double u = puct_exact(cpuct, P[q], Q[q], N[q], sq_visited, sq_fresh);
+            if (u > best_u) { best_u = u; best_j = (int)j; }       // ascending j: first maximum wins; NaN never does
+        }
+    }
+    return warp_argmax(best_u, best_j);
+}
 
 // One simulation's descent for every tree: mcts.py:243-325 (selection part of `_search`).
 // Every level costs one dependent memory round trip: the lanes load the whole edge block (priors, values,
@@ -306,124 +363,93 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
 #if !TC_TRACK_POS
         int cur = root_idx;
 #endif
+        Edge *const edges = tree_edges(ts, tree);
         while (true) {
-            EdgeBlock eb = edge_block(ts, tree, off, n);
-            EdgeRegs e[3];
-            uint32_t nsum = 0;
-            e[0].N = e[1].N = e[2].N = 0;
-            if ((uint32_t)lane < n) {
-                e[0].P = eb.P[lane];
-                e[0].Q = eb.Q[lane];
-                e[0].N = eb.N[lane];
-                e[0].child = eb.child[lane];
-                e[0].coff = eb.coff[lane];
-                e[0].meta = eb.meta[lane];
-                nsum = e[0].N;
-            }
-            if (n > 32) {                                   // wide nodes only (free moves: up to 81 edges)
-#pragma unroll
-                for (int q = 1; q < 3; ++q) {
-                    const uint32_t j = (uint32_t)lane + 32u * q;
-                    if (j < n) {
-                        e[q].P = eb.P[j];
-                        e[q].Q = eb.Q[j];
-                        e[q].N = eb.N[j];
-                        e[q].child = eb.child[j];
-                        e[q].coff = eb.coff[j];
-                        e[q].meta = eb.meta[j];
-                        nsum += e[q].N;
-                    }
-                }
-            }
-            nsum = __reduce_add_sync(FULL, nsum);                                          // Ns[s]
-
-            // PUCT over the legal edges (mcts.py:301-316).
-            int best_j = 1 << 20;
-            bool decided = false;
-#if TC_PUCT_PREFILTER
-            // The arg-max only needs the float64 values when two candidates are close.  A float32 evaluation of the same
-            // formula is within 1e-6 * (|Q| + |U|) of the exact value (conversions, approximate sqrt and division, one
-            // rounding per operation); with a ten-fold margin, every edge gets an interval [u - eps, u + eps] that contains
-            // its exact score.  If only ONE edge's upper end reaches the best lower end, that edge is the unique exact
-            // maximum — no tie can exist, so no tie-break is needed — and the ~70 float64 instructions per level (two
-            // software square roots and a division, the kernel's issue-slot hogs) are skipped.  Otherwise (exact ties of
-            // equal priors, near ties, nodes wider than a warp) the exact path below decides, as before.
+            Edge *const blk = edges + off;
+            int best_j;
+            uint32_t child, coff, meta;
             if (n <= 32u) {
+                // ---- the common node: one edge per lane, two 16-byte loads each ----
                 const bool valid = (uint32_t)lane < n;
-                // sqrt(Ns) for visited edges; sqrt(Ns + 1e-8) for fresh ones is the same float32 once Ns >= 1 (1e-8 is below
-                // half an ulp) and 1e-4 at Ns = 0; sqrt.approx is within 2^-23
-                float s0;
-                asm("sqrt.approx.f32 %0, %1;" : "=f"(s0) : "f"((float)nsum));    // (float)nsum is exact below 2^24 visits
-                const float s_fresh = nsum ? s0 : 1e-4f;
-                float u = 0.f, mag = 0.f;
+                uint4 st = make_uint4(0u, 0u, 0u, 0u), lk = make_uint4(0u, 0u, 0u, 0u);
                 if (valid) {
-                    const float cpf = (float)cpuct * (float)e[0].P;
-                    if (e[0].N) {
-                        const float qf = (float)e[0].Q;
-                        const float uf = __fdividef(cpf * s0, (float)(1u + e[0].N));
-                        u = qf + uf;
-                        mag = fabsf(qf) + fabsf(uf);
-                    } else {
-                        u = cpf * s_fresh;
-                        mag = fabsf(u);
-                    }
+                    st = edge_load_stats(blk + lane);
+                    lk = edge_load_link(blk + lane);
                 }
-                const float eps = 1e-5f * mag + 1e-30f;
-                auto okey = [](float x) {                                        // order-preserving float -> uint32
-                    const uint32_t bits = __float_as_uint(x);
-                    return bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
-                };
-                const bool finite = valid && fabsf(u) < 1e30f;                   // also false for NaN
-                const uint32_t klo = finite ? okey(u - eps) : 0u;
-                const uint32_t best_lo = __reduce_max_sync(FULL, klo);
-                const unsigned any_bad = __ballot_sync(FULL, valid && !finite);
-                const unsigned cand = __ballot_sync(FULL, finite && okey(u + eps) >= best_lo);
-                if (!any_bad && __popc(cand) == 1) {
-                    best_j = __ffs(cand) - 1;
-                    decided = true;
-                }
-            }
-#endif
-            if (!decided) {
-                const double sq_visited = nsum ? __dsqrt_rn((double)nsum) : 0.0;      // only used by edges with N > 0
-                const double sq_fresh = __dsqrt_rn(__dadd_rn((double)nsum, 1e-8));
-                double best_u = -INFINITY;
+                const uint32_t N = st.z;
+                const uint32_t nsum = __reduce_add_sync(FULL, N);                          // Ns[s]
+                const double P = u2d(lk.x, lk.y), Q = u2d(st.x, st.y);
                 best_j = 1 << 20;
-                if ((uint32_t)lane < n) {
-                    double cpp = __dmul_rn(cpuct, e[0].P);
-                    best_u = e[0].N ? __dadd_rn(e[0].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[0].N)))
-                                    : __dmul_rn(cpp, sq_fresh);
-                    best_j = lane;
-                    if (!(best_u > -INFINITY)) { best_u = -INFINITY; best_j = 1 << 20; }   // NaN / -inf is never selected (mcts.py:314)
-                }
-                if (n > 32) {
-    #pragma unroll
-                    for (int q = 1; q < 3; ++q) {
-                        const uint32_t j = (uint32_t)lane + 32u * q;
-                        if (j < n) {
-                            double cpp = __dmul_rn(cpuct, e[q].P);
-                            double u = e[q].N ? __dadd_rn(e[q].Q, __ddiv_rn(__dmul_rn(cpp, sq_visited), (double)(1u + e[q].N)))
-                                              : __dmul_rn(cpp, sq_fresh);
-                            if (u > best_u) { best_u = u; best_j = (int)j; }   // ascending j: first maximum wins
+                bool decided = false;
+#if TC_PUCT_PREFILTER
+                // PUCT over the legal edges (mcts.py:301-316).  The arg-max only needs the float64 values when two
+                // candidates are close.  A float32 evaluation of the same formula is within 1e-6 * (|Q| + |U|) of the exact
+                // value (conversions, approximate sqrt and division, one rounding per operation); with a ten-fold margin
+                // every edge gets an interval [u - eps, u + eps] that contains its exact score.  If only ONE edge's upper
+                // end reaches the best lower end, that edge is the unique exact maximum — no tie can exist, so no tie-break
+                // is needed — and the ~70 float64 instructions per level (two software square roots and a division, the
+                // kernel's issue-slot hogs) are skipped.  Otherwise (exact ties of equal priors, near ties) the exact
+                // path below decides, as it does for nodes wider than a warp.
+                {
+                    // sqrt(Ns) for visited edges; sqrt(Ns + 1e-8) for fresh ones is the same float32 once Ns >= 1 (1e-8 is
+                    // below half an ulp) and 1e-4 at Ns = 0; sqrt.approx is within 2^-23
+                    float s0;
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(s0) : "f"((float)nsum));    // (float)nsum is exact below 2^24
+                    const float s_fresh = nsum ? s0 : 1e-4f;
+                    float u = 0.f, mag = 0.f;
+                    if (valid) {
+                        const float cpf = (float)cpuct * (float)P;
+                        if (N) {
+                            const float qf = (float)Q;
+                            const float uf = __fdividef(cpf * s0, (float)(1u + N));
+                            u = qf + uf;
+                            mag = fabsf(qf) + fabsf(uf);
+                        } else {
+                            u = cpf * s_fresh;
+                            mag = fabsf(u);
                         }
                     }
-                }
-                // Warp arg-max in three REDUX steps instead of a 5-round shuffle butterfly: doubles are mapped to
-                // order-preserving unsigned keys (-0.0 folded into +0.0 first, so equal values give equal keys exactly
-                // as the reference's strict '>' sees them); max of the high words, max of the low words among the
-                // lanes that hold that high word, then the lowest edge index among the lanes that hold the maximum
-                // (edges are in action order: "lowest action index wins ties", mcts.py:314).
-                {
-                    unsigned long long key = 0ull;                 // lanes without a candidate can never win
-                    if (best_j < (1 << 20)) {
-                        long long bits = __double_as_longlong(__dadd_rn(best_u, 0.0));
-                        key = (unsigned long long)bits ^ (bits < 0 ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+                    const float eps = 1e-5f * mag + 1e-30f;
+                    auto okey = [](float x) {                                        // order-preserving float -> uint32
+                        const uint32_t bits = __float_as_uint(x);
+                        return bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+                    };
+                    const bool finite = valid && fabsf(u) < 1e30f;                   // also false for NaN
+                    const uint32_t klo = finite ? okey(u - eps) : 0u;
+                    const uint32_t best_lo = __reduce_max_sync(FULL, klo);
+                    const unsigned any_bad = __ballot_sync(FULL, valid && !finite);
+                    const unsigned cand = __ballot_sync(FULL, finite && okey(u + eps) >= best_lo);
+                    if (!any_bad && __popc(cand) == 1) {
+                        best_j = __ffs(cand) - 1;
+                        decided = true;
                     }
-                    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-                    const uint32_t mhi = __reduce_max_sync(FULL, hi);
-                    const uint32_t mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
-                    const bool top = best_j < (1 << 20) && hi == mhi && lo == mlo;
-                    best_j = (int)__reduce_min_sync(FULL, top ? (uint32_t)best_j : (uint32_t)(1 << 20));
+                }
+#endif
+                if (!decided) {
+                    const double sq_visited = nsum ? __dsqrt_rn((double)nsum) : 0.0;      // only used by edges with N > 0
+                    const double sq_fresh = __dsqrt_rn(__dadd_rn((double)nsum, 1e-8));
+                    double best_u = -INFINITY;
+                    if (valid) {
+                        best_u = puct_exact(cpuct, P, Q, N, sq_visited, sq_fresh);
+                        best_j = lane;
+                        if (!(best_u > -INFINITY)) { best_u = -INFINITY; best_j = 1 << 20; }   // NaN / -inf is never selected (mcts.py:314)
+                    }
+                    best_j = warp_argmax(best_u, best_j);
+                }
+                // the winning lane broadcasts where the child lives
+                const int src = best_j & 31;
+                child = __shfl_sync(FULL, st.w, src);
+                coff = __shfl_sync(FULL, lk.z, src);
+                meta = __shfl_sync(FULL, lk.w, src);
+            } else {
+                // ---- wide node (free move): rare; the winner's record is read back with a uniform load ----
+                best_j = select_wide(blk, n, lane, cpuct);
+                child = coff = meta = 0u;
+                if (best_j < (1 << 20)) {
+                    const uint4 st = edge_load_stats(blk + best_j), lk = edge_load_link(blk + best_j);
+                    child = st.w;
+                    coff = lk.z;
+                    meta = lk.w;
                 }
             }
             sum_legal += n;
@@ -435,15 +461,6 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             }
             if (lane == 0) path[depth] = make_uint2(off, (uint32_t)best_j | (n << 8));
             ++depth;
-
-            // the winning lane broadcasts where the child lives
-            const int wq = best_j >> 5, wl = best_j & 31;
-            uint32_t child = wq == 0 ? e[0].child : (wq == 1 ? e[1].child : e[2].child);
-            uint32_t coff = wq == 0 ? e[0].coff : (wq == 1 ? e[1].coff : e[2].coff);
-            uint32_t meta = wq == 0 ? e[0].meta : (wq == 1 ? e[1].meta : e[2].meta);
-            child = __shfl_sync(FULL, child, wl);
-            coff = __shfl_sync(FULL, coff, wl);
-            meta = __shfl_sync(FULL, meta, wl);
 
             if (child >= CHILD_TERM_BASE && child != CHILD_UNRESOLVED) {
                 int st = (int)(child - CHILD_TERM_BASE);
@@ -476,7 +493,7 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             int nst;
             warp_legal_mask(nx, lane, nam, nst);
             if (nst != 0) {
-                if (lane == 0) eb.child[best_j] = CHILD_TERM_BASE + (uint32_t)nst;
+                if (lane == 0) blk[best_j].child = CHILD_TERM_BASE + (uint32_t)nst;
                 w.leaf_kind = LEAF_TERMINAL;
                 w.leaf_value = nst == 2 ? 1e-4 : (nst == 3 ? 1.0 : -1.0);
                 terminal += 1;
@@ -490,9 +507,9 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
                 uint32_t cn, co;
                 unpack_hdr(hdr[2ull * idx], hdr[2ull * idx + 1], q, cn, co);
                 if (lane == 0) {
-                    eb.child[best_j] = (uint32_t)idx;
-                    eb.coff[best_j] = co;
-                    eb.meta[best_j] = (uint32_t)action | (cn << 8);
+                    blk[best_j].child = (uint32_t)idx;
+                    blk[best_j].coff = co;
+                    blk[best_j].meta = (uint32_t)action | (cn << 8);
                 }
                 transp += 1;
 #if TC_TRACK_POS
@@ -508,9 +525,9 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             idx = create_leaf(ts, tree, w, nx, h, free_slot, nam, lane, co, cn);
             if (idx >= 0) {
                 if (lane == 0) {
-                    eb.child[best_j] = (uint32_t)idx;
-                    eb.coff[best_j] = co;
-                    eb.meta[best_j] = (uint32_t)action | (cn << 8);
+                    blk[best_j].child = (uint32_t)idx;
+                    blk[best_j].coff = co;
+                    blk[best_j].meta = (uint32_t)action | (cn << 8);
                 }
             } else {
                 depth = 0;              // pool exhausted: drop this simulation
@@ -583,14 +600,15 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
         }
         // production mode: the policy head already masked and renormalised (float32); parity mode: mcts.py:272-275
         const double total = ts.priors_masked ? 1.0 : numpy_sum81(m, lane);
-        EdgeBlock eb = edge_block(ts, tree, off, n);
+        Edge *blk = tree_edges(ts, tree) + off;
         const bool ok = total > 0.0;
         const double uniform = __ddiv_rn(1.0, (double)n);     // (0 + valids) / np.sum(valids), mcts.py:282-283
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
+            if (am[q] == 0u) continue;                        // warp-uniform: skips the division where no lane has a move
             if ((am[q] >> lane) & 1u) {
                 int j = edge_index(am, q, lane);
-                eb.P[j] = ts.priors_masked ? m[q] : (ok ? __ddiv_rn(m[q], total) : uniform);
+                blk[j].P = ts.priors_masked ? m[q] : (ok ? __ddiv_rn(m[q], total) : uniform);
             }
         }
         x = (double)ts.eval_v[row];
@@ -604,13 +622,13 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
         int dist = path_len - e;
         double v = (dist & 1) ? -x : x;
         v = __dadd_rn(0.0, v);                                  // -0.0 normalises to +0.0 as in the reference
-        uint32_t n = pe.y >> 8, j = pe.y & 0xFFu;
-        EdgeBlock eb = edge_block(ts, tree, pe.x, n);
-        uint32_t cnt = eb.N[j];
+        const uint32_t j = pe.y & 0xFFu;
+        uint4 *rec = reinterpret_cast<uint4 *>(tree_edges(ts, tree) + pe.x + j);      // the {Q, N, child} half
+        const uint4 st = *rec;
+        const uint32_t cnt = st.z;
         double q = v;
-        if (cnt) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)cnt, eb.Q[j]), v), (double)(cnt + 1u));
-        eb.Q[j] = q;
-        eb.N[j] = cnt + 1u;
+        if (cnt) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)cnt, u2d(st.x, st.y)), v), (double)(cnt + 1u));
+        *rec = edge_pack(q, cnt + 1u, st.w);
     }
 }
 
@@ -704,7 +722,7 @@ __global__ void k_root_counts(TreeStore ts, uint32_t *__restrict__ counts, doubl
         int status;
         warp_legal_mask(p, lane, am, status);
     }
-    EdgeBlock eb = edge_block(ts, tree, off, n);
+    const Edge *blk = tree_edges(ts, tree) + off;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         int a = lane + 32 * q;
@@ -713,8 +731,8 @@ __global__ void k_root_counts(TreeStore ts, uint32_t *__restrict__ counts, doubl
             double qv = nan("");
             if (have && ((am[q] >> lane) & 1u)) {
                 int j = edge_index(am, q, lane);
-                cnt = eb.N[j];
-                if (cnt) qv = eb.Q[j];
+                cnt = blk[j].N;
+                if (cnt) qv = blk[j].Q;
             }
             if (counts) counts[81 * (size_t)tree + a] = cnt;
             if (qout) qout[81 * (size_t)tree + a] = qv;

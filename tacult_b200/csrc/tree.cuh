@@ -14,11 +14,13 @@
 // Layout in HBM (one warp owns one tree, so nothing below needs atomics):
 //   node header  32 B : mine[3] occ[3] meta(last_square+1 | n_edges<<8) edge_off   — immutable; only read when
 //                       a node is expanded or looked up, never on the way down
-//   edge block  32n B : P[n] f64 | Q[n] f64 | N[n] u32 | child[n] u32 | coff[n] u32 | meta[n] u32, edges in
-//                       action order.  meta = action | n_edges(child)<<8, coff = edge block of the child: an edge
-//                       carries everything needed to step to the child's edge block, so one level of the descent
-//                       is ONE dependent memory round trip.  Ns[s] is not stored: it always equals the sum of the
-//                       node's edge counts (both are incremented together, mcts.py:333-340).
+//   edge block  32n B : n records of 32 bytes, edges in action order, each two 16-byte halves a lane moves with ONE
+//                       vector load / store:  { Q f64, N u32, child u32 } — what the backup reads and rewrites — and
+//                       { P f64, coff u32, meta u32 } — written once (creation, expansion).  meta = action |
+//                       n_edges(child)<<8, coff = edge block of the child: an edge carries everything needed to step to
+//                       the child's edge block, so one level of the descent is ONE dependent memory round trip (two
+//                       16-byte loads per lane).  Ns[s] is not stored: it always equals the sum of the node's edge
+//                       counts (both are incremented together, mcts.py:333-340).
 //   hash table   4 B/slot, per tree, open addressing, entry = tag(12) | node index + 1 (20)
 #pragma once
 #include "common.cuh"
@@ -74,27 +76,29 @@ struct TreeStore {
     int priors_masked;          // eval_pi is already masked + renormalised (TC_EVAL_NET_BF16_MASKED): store it as is
 };
 
-struct EdgeBlock {
-    double *P;
-    double *Q;
-    uint32_t *N;
-    uint32_t *child;
-    uint32_t *coff;
-    uint32_t *meta;
+struct __align__(16) Edge {        // 32 bytes
+    double Q;                      // mean value of the edge (mcts.py:156), meaningful when N > 0
+    uint32_t N;                    // visit count
+    uint32_t child;                // CHILD_UNRESOLVED, a node index, or CHILD_TERM_BASE + status
+    double P;                      // prior (float64, as the reference stores it)
+    uint32_t coff;                 // edge block of the child
+    uint32_t meta;                 // action | n_edges(child) << 8
 };
+static_assert(sizeof(Edge) == 32, "edge record is two 16-byte halves");
 
 #ifdef __CUDACC__
-__device__ __forceinline__ EdgeBlock edge_block(const TreeStore &ts, int tree, uint32_t edge_off, uint32_t n)
+// first edge of a tree's pool; a node's block is tree_edges(...) + edge_off
+__device__ __forceinline__ Edge *tree_edges(const TreeStore &ts, int tree)
 {
-    unsigned long long *base = ts.edge_mem + 4ull * ((unsigned long long)tree * ts.capE + edge_off);
-    EdgeBlock b;
-    b.P = reinterpret_cast<double *>(base);
-    b.Q = b.P + n;
-    b.N = reinterpret_cast<uint32_t *>(b.Q + n);
-    b.child = b.N + n;
-    b.coff = b.child + n;
-    b.meta = b.coff + n;
-    return b;
+    return reinterpret_cast<Edge *>(ts.edge_mem) + (size_t)tree * ts.capE;
+}
+// the halves as 16-byte vectors: x,y = the double, z,w = the two words
+__device__ __forceinline__ uint4 edge_load_stats(const Edge *e) { return *reinterpret_cast<const uint4 *>(e); }
+__device__ __forceinline__ uint4 edge_load_link(const Edge *e) { return *(reinterpret_cast<const uint4 *>(e) + 1); }
+__device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+__device__ __forceinline__ uint4 edge_pack(double d, uint32_t a, uint32_t b)
+{
+    return make_uint4((uint32_t)__double2loint(d), (uint32_t)__double2hiint(d), a, b);
 }
 #endif
 
