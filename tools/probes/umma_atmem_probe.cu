@@ -2,7 +2,6 @@
 //   (1) A from shared memory, M = 128 (the product trunk's shape): cycles per UMMA at N = 32 / 64      [baseline]
 //   (2) A from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): same shapes — no A fetch from shared memory
 //   (3) M = 64 from shared memory: half the A bytes per instruction
-//   (4) the transposed formulation: A = weights resident in TMEM, B = a [256 x 16] activation tile in shared memory
 // Four issuing threads, one accumulator each (the aggregate rate of the tensor pipe, as in umma_rate_probe.cu).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/umma_atmem_probe umma_atmem_probe.cu
 #include <cstdio>
@@ -86,7 +85,5 @@ int main()
             printf("%s, N = %3d, K = 16: %s  %.1f cycles per UMMA (four issuers, aggregate)  -> %.0f MAC/clk\n", names[mode], n,
                    cudaGetErrorString(e), (double)h / (4.0 * iters), (mode == 2 ? 64.0 : 128.0) * n * 16 / ((double)h / (4.0 * iters)));
         }
-    // (4) transposed: weights [128 x 16] in TMEM, activations [N x 16] in shared memory, N = 128 / 256 (one accumulator per issuer
-    // needs 4 x N columns: N = 96 above is the widest that leaves room; here two issuers with N = 192)
     return 0;
 }
