@@ -16,6 +16,8 @@
 // mcts.py:272-275 in float32) + tanh epilogue.  That removes a kernel boundary (launch, drain, TMEM / barrier set-up:
 // 12 us for a 12 MFLOP GEMM) from every simulation.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "nn_bf16.cuh"
 #include "rules.cuh"
@@ -204,6 +206,7 @@ struct HParams {
     const uint32_t *states;  // packed leaf positions (masked mode), else null
     int masked;
     int pdl_trigger;
+    long long *marks;        // optional (TACULT_FC1_TIMELINE): clock64 stamps of one epilogue thread of every cluster's CTA 0
 };
 
 __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ CUtensorMap tmA,
@@ -220,6 +223,9 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
 
     griddep_launch(P.pdl_trigger);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long *mk = (P.marks && threadIdx.x == 64 && (blockIdx.x & 1) == 0 && (blockIdx.x >> 1) < 256)
+                        ? P.marks + 16 * (blockIdx.x >> 1) : nullptr;
+    if (mk) mk[0] = clock64();
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(tfull, 1);
@@ -235,7 +241,9 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (mk) mk[1] = clock64();
     griddep_wait();
+    if (mk) mk[2] = clock64();
 
     int count = P.batch;
     if (P.count_dev) count = min(count, *P.count_dev);
@@ -285,6 +293,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
             }
         } else {
             mbar_wait(tfull, 0);
+            if (mk) mk[3] = clock64();
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
             tmem_ld32(t_base, a0);
@@ -294,6 +303,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
         }
         __syncwarp();
         cluster_sync_all();
+        if (mk) mk[4] = clock64();
         const int quarter = warp & 3;
         const int r = 32 * quarter + lane;
         float *part = reinterpret_cast<float *>(smem);    // [64 columns][128 rows] in CTA 0 (32 KB of the drained ring)
@@ -306,6 +316,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
             }
         }
         cluster_sync_all();
+        if (mk) mk[5] = clock64();
         if (warp >= 2 && rank == 0) {
             const int q = 128 * mt + r;
             if (q < count) {
@@ -329,6 +340,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
         }
         if (rank == 0) {
             // publish this slice; whoever completes the row tile runs its heads
+            if (mk) mk[6] = clock64();
             __syncthreads();
             if (threadIdx.x == 0) {
                 __threadfence();
@@ -342,6 +354,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
             }
             __syncthreads();
             run_heads = *s_last != 0;
+            if (mk) { mk[7] = clock64(); mk[12] = run_heads; mk[13] = n_done; }
         }
     }
     if (run_heads) {
@@ -395,6 +408,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
             }
             mbar_wait(hfull, 0);
             tc_fence_after();
+            if (mk) mk[8] = clock64();
             const uint32_t t_base = tmem_base + ((uint32_t)(32 * quarter) << 16) + 64u;
             uint32_t h0[32], h1[32], h2[32];
             tmem_ld32(t_base, h0);
@@ -442,6 +456,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
             }
         }
     }
+    if (mk) mk[9] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS_H);
@@ -472,6 +487,12 @@ int launch_fc1_heads(const CUtensorMap &a, const CUtensorMap &b, const CUtensorM
     P.states = states;
     P.masked = masked;
     P.pdl_trigger = pdl_trigger_enabled();
+    static long long *marks_dev = nullptr;
+    if (getenv("TACULT_FC1_TIMELINE")) {
+        if (!marks_dev) cudaMalloc(&marks_dev, 16 * 256 * sizeof(long long));
+        cudaMemsetAsync(marks_dev, 0, 16 * 256 * sizeof(long long), st);
+        P.marks = marks_dev;
+    }
     const size_t smem = fc1_heads_smem(stages);
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -495,6 +516,27 @@ int launch_fc1_heads(const CUtensorMap &a, const CUtensorMap &b, const CUtensorM
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     TC_CUDA(cudaLaunchKernelEx(&cfg, fc1::k_fc1_heads, a, b, emb_map, head_w, P));
+    if (P.marks) {          // debugging aid: where a launch spends its time, per cluster (cycles since that CTA's entry)
+        static long long h[16 * 256];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, marks_dev, sizeof h, cudaMemcpyDeviceToHost);
+        long long sum[10] = {0}, heads_n = 0, n = 0, t_min = 0, t_max = 0;
+        for (int t = 0; t < 256; ++t) {
+            const long long *m = h + 16 * t;
+            if (m[0] == 0 || m[9] == 0) continue;
+            ++n;
+            for (int k = 1; k < 10; ++k) sum[k] += (m[k] ? m[k] - m[0] : 0);
+            heads_n += m[12];
+            if (t_min == 0 || m[0] < t_min) t_min = m[0];
+            if (m[9] > t_max) t_max = m[9];
+        }
+        if (n)
+            fprintf(stderr, "[fc1 marks] %lld clusters (%lld ran heads); mean cycles since CTA entry: prologue %lld | dep wait "
+                    "over %lld | fc1 accumulators done %lld | cluster sync 1 %lld | partials landed %lld | slice stored "
+                    "%lld | arrival known %lld | heads accumulator done (heads CTAs) %lld | exit %lld ; first entry -> last "
+                    "exit %lld\n", n, heads_n, sum[1] / n, sum[2] / n, sum[3] / n, sum[4] / n, sum[5] / n, sum[6] / n,
+                    sum[7] / n, heads_n ? sum[8] / heads_n : 0, sum[9] / n, t_max - t_min);
+    }
     return TC_OK;
 }
 
