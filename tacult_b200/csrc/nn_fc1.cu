@@ -520,22 +520,20 @@ int launch_fc1_heads(const CUtensorMap &a, const CUtensorMap &b, const CUtensorM
         static long long h[16 * 256];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, marks_dev, sizeof h, cudaMemcpyDeviceToHost);
-        long long sum[10] = {0}, heads_n = 0, n = 0, t_min = 0, t_max = 0;
+        long long sum[10] = {0}, heads_n = 0, n = 0;
         for (int t = 0; t < 256; ++t) {
             const long long *m = h + 16 * t;
             if (m[0] == 0 || m[9] == 0) continue;
             ++n;
             for (int k = 1; k < 10; ++k) sum[k] += (m[k] ? m[k] - m[0] : 0);
             heads_n += m[12];
-            if (t_min == 0 || m[0] < t_min) t_min = m[0];
-            if (m[9] > t_max) t_max = m[9];
         }
         if (n)
             fprintf(stderr, "[fc1 marks] %lld clusters (%lld ran heads); mean cycles since CTA entry: prologue %lld | dep wait "
                     "over %lld | fc1 accumulators done %lld | cluster sync 1 %lld | partials landed %lld | slice stored "
-                    "%lld | arrival known %lld | heads accumulator done (heads CTAs) %lld | exit %lld ; first entry -> last "
-                    "exit %lld\n", n, heads_n, sum[1] / n, sum[2] / n, sum[3] / n, sum[4] / n, sum[5] / n, sum[6] / n,
-                    sum[7] / n, heads_n ? sum[8] / heads_n : 0, sum[9] / n, t_max - t_min);
+                    "%lld | arrival known %lld | heads accumulator done (heads CTAs) %lld | exit (all CTAs) %lld\n", n,
+                    heads_n, sum[1] / n, sum[2] / n, sum[3] / n, sum[4] / n, sum[5] / n, sum[6] / n, sum[7] / n,
+                    heads_n ? sum[8] / heads_n : 0, sum[9] / n);
     }
     return TC_OK;
 }
