@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2);
     int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
-    griddep_launch(P.pdl_trigger);
+    griddep_launch(P.pdl_trigger == 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long *mk = (P.marks && threadIdx.x == 64 && (blockIdx.x & 1) == 0 && (blockIdx.x >> 1) < 256)
                         ? P.marks + 16 * (blockIdx.x >> 1) : nullptr;
@@ -357,6 +357,9 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
             if (mk) { mk[7] = clock64(); mk[12] = run_heads; mk[13] = n_done; }
         }
     }
+    // late trigger (TACULT_PDL_TRIGGER=2): the fc1 part of this CTA is over; the descent kernel's blocks may take the SMs
+    // that CTAs without a heads tile free, and park in griddep_wait until the heads tiles are done
+    if (threadIdx.x == 0) griddep_launch(P.pdl_trigger == 2);
     if (run_heads) {
         // ===== heads of row tile mt: [128 x E] (just written by E/64 clusters, L2 resident) x [96 x E]^T =====
         const int h_chunks = P.n_blocks;                  // E / 64

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
 
     // ---- prologue that depends on nothing the previous kernel wrote: it overlaps that kernel's tail (programmatic
     //      dependent launch, common.cuh) ----
-    griddep_launch(P.pdl_trigger);
+    griddep_launch(P.pdl_trigger == 1);
     // optional marks of CTA 0 (TACULT_FUSED_TIMELINE): kernel entry, prologue done, dependency wait over, first planes
     // encoded, every group done, exit — where a launch spends the time that is not layer work
     long long *marks = (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? P.timeline + 8 * 32 : nullptr;
@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
     const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
     const int p_begin = min(count, (int)blockIdx.x * per), p_end = min(count, p_begin + per);
     const int n_my_groups = (p_end - p_begin + P.G - 1) / P.G;
+    if (n_my_groups == 0 && threadIdx.x == 0) griddep_launch(P.pdl_trigger == 2);
     if (threadIdx.x == 0) {
         for (int t = 0; t < MAX_TILES; ++t) mbar_init(tdone + t, 1);
         for (int t = 0; t < 2 * MAX_TILES; ++t) mbar_init(aready + t, 4);
@@ -244,6 +245,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
             uint8_t *dst = to_y ? Y : X;
             const bool last = l == n_layers - 1;
             const bool residual = l > 0 && !to_y;
+            // late trigger (TACULT_PDL_TRIGGER=2): once every CTA is in the last layer of its last group, fc1's CTAs may
+            // become resident on the SMs that free up first and run their prologue behind this kernel's tail
+            if (last && group == n_my_groups - 1 && threadIdx.x == 0) griddep_launch(P.pdl_trigger == 2);
             if (warp == 0) {
                 if (lane == 0) {
                     // stream the NEXT layer's weights into the other buffer once the layer before this one (its

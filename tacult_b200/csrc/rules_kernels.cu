@@ -122,29 +122,53 @@ __global__ void k_rules_playouts(uint64_t seed, uint64_t first_game, int n, int 
 
 using namespace tc;
 
+namespace {
+// Per-thread device scratch of the stateless rules hooks, grown on demand and kept: a hook called once per ply must not
+// pay five cudaMalloc / cudaFree pairs per call.  One arena per host thread and device, carved into 256-byte aligned parts.
+struct Scratch {
+    int device = -1;
+    uint8_t *base = nullptr;
+    size_t bytes = 0;
+    ~Scratch() { if (base) cudaFree(base); }
+    cudaError_t reserve(size_t need)
+    {
+        int dev = 0;
+        cudaError_t err = cudaGetDevice(&dev);
+        if (err != cudaSuccess) return err;
+        if (dev == device && need <= bytes) return cudaSuccess;
+        if (base) { cudaFree(base); base = nullptr; bytes = 0; }
+        device = dev;
+        need = (need + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+        err = cudaMalloc((void **)&base, need);
+        if (err == cudaSuccess) bytes = need;
+        return err;
+    }
+};
+thread_local Scratch g_scratch;
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
 extern "C" int tc_rules_step(int n, const uint32_t *states_host, const int8_t *actions_host,
                              uint32_t *out_states_host, int8_t *status_host)
 {
     TC_CHECK(n >= 0 && (n == 0 || (states_host && actions_host && out_states_host && status_host)), TC_EINVAL,
              "tc_rules_step: null buffer");
     if (n == 0) return TC_OK;
-    DevBuf<uint32_t> in, out;
-    DevBuf<int8_t> act, st;
-    DevBuf<int> bad;
-    TC_CUDA(in.alloc(8 * (size_t)n));
-    TC_CUDA(out.alloc(8 * (size_t)n));
-    TC_CUDA(act.alloc(n));
-    TC_CUDA(st.alloc(n));
-    TC_CUDA(bad.alloc(1));
-    TC_CUDA(cudaMemcpy(in.p, states_host, in.bytes(), cudaMemcpyHostToDevice));
-    TC_CUDA(cudaMemcpy(act.p, actions_host, act.bytes(), cudaMemcpyHostToDevice));
-    TC_CUDA(cudaMemset(bad.p, 0, sizeof(int)));
-    k_rules_step<<<ceil_div(n, 256), 256>>>(n, in.p, act.p, out.p, st.p, bad.p);
+    const size_t sb = align256(32 * (size_t)n), ab = align256((size_t)n);
+    TC_CUDA(g_scratch.reserve(2 * sb + 2 * ab + 256));
+    uint32_t *in = reinterpret_cast<uint32_t *>(g_scratch.base), *out = reinterpret_cast<uint32_t *>(g_scratch.base + sb);
+    int8_t *act = reinterpret_cast<int8_t *>(g_scratch.base + 2 * sb), *st = act + ab;
+    int *bad = reinterpret_cast<int *>(g_scratch.base + 2 * sb + 2 * ab);
+    TC_CUDA(cudaMemcpy(in, states_host, 32 * (size_t)n, cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemcpy(act, actions_host, (size_t)n, cudaMemcpyHostToDevice));
+    TC_CUDA(cudaMemset(bad, 0, sizeof(int)));
+    k_rules_step<<<ceil_div(n, 256), 256>>>(n, in, act, out, st, bad);
     TC_CUDA(cudaGetLastError());
     int nbad = 0;
-    TC_CUDA(cudaMemcpy(out_states_host, out.p, out.bytes(), cudaMemcpyDeviceToHost));
-    TC_CUDA(cudaMemcpy(status_host, st.p, st.bytes(), cudaMemcpyDeviceToHost));
-    TC_CUDA(cudaMemcpy(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemcpy(out_states_host, out, 32 * (size_t)n, cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemcpy(status_host, st, (size_t)n, cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemcpy(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost));
     TC_CHECK(nbad == 0, TC_EILLEGAL, "tc_rules_step: %d illegal move(s) requested", nbad);
     return TC_OK;
 }
@@ -154,21 +178,20 @@ static int mask_obs_common(int n, const uint32_t *states_host, uint8_t *mask_hos
 {
     TC_CHECK(n >= 0 && (n == 0 || states_host), TC_EINVAL, "rules hook: null states");
     if (n == 0) return TC_OK;
-    DevBuf<uint32_t> in;
-    DevBuf<uint8_t> mask;
-    DevBuf<float> obs;
-    DevBuf<int8_t> st;
-    TC_CUDA(in.alloc(8 * (size_t)n));
-    if (mask_host) TC_CUDA(mask.alloc(81 * (size_t)n));
-    if (obs_host) TC_CUDA(obs.alloc(324 * (size_t)n));
-    if (status_host) TC_CUDA(st.alloc(n));
-    TC_CUDA(cudaMemcpy(in.p, states_host, in.bytes(), cudaMemcpyHostToDevice));
+    const size_t sb = align256(32 * (size_t)n), mb = mask_host ? align256(81 * (size_t)n) : 0,
+                 ob = obs_host ? align256(324 * sizeof(float) * (size_t)n) : 0, tb = status_host ? align256((size_t)n) : 0;
+    TC_CUDA(g_scratch.reserve(sb + mb + ob + tb));
+    uint32_t *in = reinterpret_cast<uint32_t *>(g_scratch.base);
+    uint8_t *mask = mask_host ? g_scratch.base + sb : nullptr;
+    float *obs = obs_host ? reinterpret_cast<float *>(g_scratch.base + sb + mb) : nullptr;
+    int8_t *st = status_host ? reinterpret_cast<int8_t *>(g_scratch.base + sb + mb + ob) : nullptr;
+    TC_CUDA(cudaMemcpy(in, states_host, 32 * (size_t)n, cudaMemcpyHostToDevice));
     int threads = 256, warps_per_block = threads / 32;
-    k_rules_mask_obs<<<ceil_div(n, warps_per_block), threads>>>(n, in.p, mask.p, obs.p, st.p);
+    k_rules_mask_obs<<<ceil_div(n, warps_per_block), threads>>>(n, in, mask, obs, st);
     TC_CUDA(cudaGetLastError());
-    if (mask_host) TC_CUDA(cudaMemcpy(mask_host, mask.p, mask.bytes(), cudaMemcpyDeviceToHost));
-    if (obs_host) TC_CUDA(cudaMemcpy(obs_host, obs.p, obs.bytes(), cudaMemcpyDeviceToHost));
-    if (status_host) TC_CUDA(cudaMemcpy(status_host, st.p, st.bytes(), cudaMemcpyDeviceToHost));
+    if (mask_host) TC_CUDA(cudaMemcpy(mask_host, mask, 81 * (size_t)n, cudaMemcpyDeviceToHost));
+    if (obs_host) TC_CUDA(cudaMemcpy(obs_host, obs, 324 * sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (status_host) TC_CUDA(cudaMemcpy(status_host, st, (size_t)n, cudaMemcpyDeviceToHost));
     return TC_OK;
 }
 
@@ -195,10 +218,10 @@ extern "C" int tc_rules_playouts(uint64_t seed, uint64_t first_game, int n, int 
 {
     TC_CHECK(n >= 0 && (n == 0 || out_host), TC_EINVAL, "tc_rules_playouts: null output");
     if (n == 0) return TC_OK;
-    DevBuf<tc_playout_result> out;
-    TC_CUDA(out.alloc(n));
-    k_rules_playouts<<<ceil_div(n, 128), 128>>>(seed, first_game, n, max_plies, out.p);
+    TC_CUDA(g_scratch.reserve(sizeof(tc_playout_result) * (size_t)n));
+    tc_playout_result *out = reinterpret_cast<tc_playout_result *>(g_scratch.base);
+    k_rules_playouts<<<ceil_div(n, 128), 128>>>(seed, first_game, n, max_plies, out);
     TC_CUDA(cudaGetLastError());
-    TC_CUDA(cudaMemcpy(out_host, out.p, out.bytes(), cudaMemcpyDeviceToHost));
+    TC_CUDA(cudaMemcpy(out_host, out, sizeof(tc_playout_result) * (size_t)n, cudaMemcpyDeviceToHost));
     return TC_OK;
 }

@@ -665,7 +665,7 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
 
 __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
 {
-    griddep_launch(ts.pdl_trigger);
+    griddep_launch(ts.pdl_trigger == 1);
     griddep_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && ts.eval_count_next) *ts.eval_count_next = 0;
     const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
 // expansion/backup, then walks down again while the path's nodes are still in cache.
 __global__ void __launch_bounds__(128, 7) k_backup_select(TreeStore ts, double cpuct)
 {
-    griddep_launch(ts.pdl_trigger);
+    griddep_launch(ts.pdl_trigger == 1);
     griddep_wait();
     // the other counter of the pair was last read by the evaluator kernels of the previous simulation, which have
     // completed; the next simulation's descent starts counting from zero without a memset node in the stream
