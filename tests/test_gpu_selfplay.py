@@ -173,3 +173,60 @@ def test_device_drain_and_example_kernel_match_the_host_path():
     assert set(np.unique(np.abs(want_z))) <= {np.float32(1.0), np.float32(1e-4)}
     onehot = host_recs["tau_one"] == 0
     assert (pi.shape[1] == 81) and np.array_equal(want_pi[::8][onehot].argmax(1), host_recs["action"][onehot])
+
+
+def test_full_size_iteration_invariants_bf16():
+    """BASELINE config C3's width (4096 trees, bf16 production evaluator, games to completion — fewer sims to keep the
+    test short): size-independent properties of the whole iteration, checked by replaying every recorded move through
+    the rules hooks: consecutive plies of a game chain through tc_rules_step, visit counts live on legal moves only and
+    add up to at least sims - 1, the move played was visited, the recorded outcome is the terminal status of the last
+    position seen from each record's player, and exactly numEnvs games were played (coach.py:175)."""
+    import torch
+    from tacult_b200.network import TrunkNet
+    envs, sims = 4096, 24
+    torch.manual_seed(3)
+    sd = {k: v.detach().numpy().copy() for k, v in TrunkNet(32, 3, 256, dropout=0.2).eval().state_dict().items()}
+    eng = tb.Engine(envs, sims * 82 + 64)
+    eng.load_weights(sd)
+    eng.set_evaluator(tb._lib.EVAL_NET_BF16)
+    eng.selfplay_begin(sims, 2.4, 10, seed=77, auto_reset=False)
+    for _ in range(81):
+        eng.selfplay_step(1)
+        if eng.selfplay_stats()["games_finished"] == envs:
+            break
+    eng.selfplay_sync()
+    st = eng.selfplay_stats()
+    recs = eng.selfplay_drain()
+    assert st["games_finished"] == envs and len(recs) == st["plies"] and st["sims"] == st["plies"] * sims
+    assert st["first_player_wins"] + st["second_player_wins"] + st["draws"] == envs
+    order = np.lexsort((recs["ply"], recs["env"]))
+    recs = recs[order]
+    env, ply = recs["env"], recs["ply"]
+    first = np.r_[True, env[1:] != env[:-1]]
+    last = np.r_[first[1:], True]
+    assert sorted(set(env.tolist())) == list(range(envs)) and (ply[first] == 0).all()
+    assert (ply[~first] == ply[np.flatnonzero(~first) - 1] + 1).all()                 # plies 0..n-1 of every game
+    assert (recs["state"][first] == 0).all() and (recs["player"][first] == 1).all()   # initial position, player +1
+    counts = recs["counts"].astype(np.int64)
+    legal = tb.rules_legal_mask(np.ascontiguousarray(recs["state"])).astype(bool)
+    assert (counts[~legal] == 0).all() and (counts.sum(1) >= sims - 1).all()
+    act = recs["action"].astype(np.int64)
+    assert (counts[np.arange(len(recs)), act] > 0).all()
+    greedy = recs["tau_one"] == 0
+    assert (counts[np.arange(len(recs)), act][greedy] == counts.max(1)[greedy]).all()   # tau = 0: an arg-max was played
+    assert ((recs["tau_one"] == 1) == (ply + 1 < 10)).all()                              # coach.py:124-125
+    nxt, status = tb.rules_step(np.ascontiguousarray(recs["state"]), recs["action"])
+    inner = np.flatnonzero(~last)
+    assert (status[inner] == 0).all() and (nxt[inner] == recs["state"][inner + 1]).all()
+    assert (recs["player"][inner + 1] == -recs["player"][inner]).all()
+    end = np.flatnonzero(last)
+    assert (status[end] != 0).all()
+    # outcome per game: status of the final position is seen by the player who did NOT make the last move
+    mover = recs["player"][end].astype(np.int64)
+    winner = np.where(status[end] == tb._lib.LOST, mover, np.where(status[end] == tb._lib.WON, -mover, 0))
+    game_of = np.cumsum(first) - 1
+    w = winner[game_of]
+    want_sign = np.where(w == 0, np.where(recs["player"] == -mover[game_of], 1, -1), np.where(recs["player"] == w, 1, -1))
+    assert (recs["z_sign"] == want_sign).all()
+    assert ((recs["finished"] == 2) == (w == 0)).all() and (recs["finished"] >= 1).all()
+    assert int((winner == 1).sum()) == st["first_player_wins"] and int((winner == 0).sum()) == st["draws"]
