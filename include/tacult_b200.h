@@ -100,6 +100,10 @@ int         tc_abi_version(void);
 /* free / total bytes of HBM on `device` (used by the host side to size tree pools) */
 int         tc_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 const char *tc_last_error(void);
+/* page-locked host memory for the *_host buffers of this API (optional: any host pointer works, pinned ones copy faster
+ * and without a staging pass); free with tc_host_free */
+int         tc_host_alloc(size_t bytes, void **out);
+int         tc_host_free(void *p);
 
 /* ---- rules engine hooks: replace utac_gym.core.GameState methods (external C++ `utac`;
  *      call sites /root/reference/src/tacult/utac_game.py:45-46,62,75-81,248) -------------- */

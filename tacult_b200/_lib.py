@@ -120,6 +120,8 @@ _gsp = ctypes.POINTER(GameStateStruct)
 SYMBOLS = {
     "tc_abi_version": (_i, []),
     "tc_last_error": (ctypes.c_char_p, []),
+    "tc_host_alloc": (_i, [_sz, ctypes.POINTER(_vp)]),
+    "tc_host_free": (_i, [_vp]),
     "tc_device_memory": (_i, [_i, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "tc_gs_init": (None, [_gsp]),
     "tc_gs_rederive": (None, [_gsp]),
@@ -194,6 +196,28 @@ def load():
 def check(code):
     if code != TC_OK:
         raise TacultError(code, load().tc_last_error().decode("utf-8", "replace"))
+
+
+class PinnedArray:
+    """A numpy array over page-locked host memory (tc_host_alloc); the memory lives as long as this object."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = ctypes.c_void_p()
+        check(self._lib.tc_host_alloc(max(n, 1), ctypes.byref(self._ptr)))
+        buf = (ctypes.c_uint8 * max(n, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self.array[...] = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None) is not None and self._ptr.value:
+                self.array = None
+                self._lib.tc_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
 
 
 def ptr(array):

@@ -142,6 +142,21 @@ static int check_device_errors(tc_engine *e)
 extern "C" int tc_abi_version(void) { return TC_ABI_VERSION; }
 extern "C" const char *tc_last_error(void) { return g_error; }
 
+extern "C" int tc_host_alloc(size_t bytes, void **out)
+{
+    TC_CHECK(out != nullptr, TC_EINVAL, "tc_host_alloc: null output");
+    *out = nullptr;
+    if (bytes == 0) return TC_OK;
+    TC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return TC_OK;
+}
+
+extern "C" int tc_host_free(void *p)
+{
+    if (p) TC_CUDA(cudaFreeHost(p));
+    return TC_OK;
+}
+
 extern "C" int tc_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes)
 {
     TC_CHECK(free_bytes && total_bytes, TC_EINVAL, "tc_device_memory: null output");

@@ -141,8 +141,11 @@ class Engine:
     def search(self, num_sims, cpuct):
         check(self.lib.tc_search(self.handle, int(num_sims), float(cpuct)))
 
-    def root_counts(self):
-        out = np.empty((self.num_envs, 81), dtype=np.uint32)
+    def root_counts(self, out=None):
+        """Root edge visit counts u32[num_envs, 81]; `out` = a caller-owned (e.g. pinned) buffer to fill and return."""
+        if out is None:
+            out = np.empty((self.num_envs, 81), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.shape == (self.num_envs, 81) and out.flags["C_CONTIGUOUS"]
         check(self.lib.tc_root_counts(self.handle, ptr(out)))
         return out
 
@@ -228,12 +231,17 @@ class Engine:
 
 
 # -- stateless rules hooks ---------------------------------------------------------------------
-def rules_step(states, actions):
+def rules_step(states, actions, out=None, status=None):
+    """out / status: optional caller-owned (e.g. pinned) result buffers u32[n, 8] / i8[n]."""
     lib = _lib.load()
     states = np.ascontiguousarray(states, dtype=np.uint32).reshape(-1, 8)
     actions = np.ascontiguousarray(actions, dtype=np.int8).reshape(-1)
-    out = np.empty_like(states)
-    status = np.empty(states.shape[0], dtype=np.int8)
+    if out is None:
+        out = np.empty_like(states)
+    if status is None:
+        status = np.empty(states.shape[0], dtype=np.int8)
+    assert out.shape == states.shape and out.dtype == np.uint32 and out.flags["C_CONTIGUOUS"]
+    assert status.shape == (states.shape[0],) and status.dtype == np.int8
     check(lib.tc_rules_step(states.shape[0], ptr(states), ptr(actions), ptr(out), ptr(status)))
     return out, status
 
