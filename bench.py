@@ -494,10 +494,11 @@ def run_dropin(a, eng, tb, torch, evaluator):
         nxt, st = tb.rules_step(states, acts)
         states[:] = nxt
         ply_no += 1
-        for i in np.flatnonzero(st != 0):
-            states[i] = 0
-            ply_no[i] = 0
-            mcts.reset(int(i))
+        done = np.flatnonzero(st != 0)
+        if done.size:
+            states[done] = 0
+            ply_no[done] = 0
+            mcts.engine.reset_envs(done)
     from tacult_b200.mcts import action_probs_from_counts
     counts = mcts.engine.root_counts().astype(np.int64)
     t2 = time.perf_counter()
@@ -734,10 +735,11 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
         nxt, st = tb.rules_step(states, acts.astype(np.int8), out=next_buf, status=status_buf)
         states[:] = nxt
         ply_no[:] += 1
-        for i in np.flatnonzero(st != 0):      # finished game: fresh tree, initial position
-            states[i] = 0
-            ply_no[i] = 0
-            eng.reset(int(i))
+        done = np.flatnonzero(st != 0)         # finished games: fresh trees (VectorizedMCTS.reset), initial position
+        if done.size:
+            states[done] = 0
+            ply_no[done] = 0
+            eng.reset_envs(done)
         return E * sims
 
     for _ in range(a.warmup):

@@ -157,6 +157,7 @@ int tc_destroy(tc_engine *e);
 int tc_set_stream(tc_engine *e, void *cuda_stream);                /* cudaStream_t; NULL = engine-owned stream */
 int tc_sync(tc_engine *e);                                         /* waits for everything enqueued on that stream */
 int tc_reset(tc_engine *e, int env);                               /* VectorizedMCTS.reset(i) mcts.py:165-172; env<0 = all */
+int tc_reset_envs(tc_engine *e, int n, const int32_t *envs_host);  /* the same for a list of envs, one launch */
 int tc_set_hash_evaluator(tc_engine *e, uint64_t salt, int pi_levels, int v_levels);
 int tc_set_evaluator(tc_engine *e, int evaluator);
 /* roots for the next tc_search: canonicalBoards of getActionProbs (mcts.py:175).  active[i]==0 marks a

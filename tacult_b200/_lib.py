@@ -141,6 +141,7 @@ SYMBOLS = {
     "tc_set_stream": (_i, [_vp, _vp]),
     "tc_sync": (_i, [_vp]),
     "tc_reset": (_i, [_vp, _i]),
+    "tc_reset_envs": (_i, [_vp, _i, _vp]),
     "tc_set_hash_evaluator": (_i, [_vp, _u64, _i, _i]),
     "tc_set_evaluator": (_i, [_vp, _i]),
     "tc_set_roots": (_i, [_vp, _vp, _vp, _vp, _vp]),

@@ -85,6 +85,7 @@ struct tc_engine {
     DevBuf<uint16_t> fld_board, fld_occ;
     DevBuf<int8_t> fld_last;
     DevBuf<double> root_q;
+    DevBuf<int32_t> reset_list;
     // evaluation log
     DevBuf<uint32_t> log_states;
     DevBuf<float> log_pi, log_v;
@@ -341,6 +342,22 @@ extern "C" int tc_reset(tc_engine *e, int env)
     launch_reset(e->ts, env, e->stream);
     e->launches += 1;
     TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+extern "C" int tc_reset_envs(tc_engine *e, int n, const int32_t *envs_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(n >= 0 && (n == 0 || envs_host), TC_EINVAL, "tc_reset_envs: null list");
+    if (n == 0) return TC_OK;
+    for (int i = 0; i < n; ++i)
+        TC_CHECK(envs_host[i] >= 0 && envs_host[i] < e->ts.E, TC_EINVAL, "tc_reset_envs: env %d out of range", envs_host[i]);
+    if ((size_t)n > e->reset_list.n) TC_CUDA(e->reset_list.alloc(std::max<size_t>((size_t)n, (size_t)e->ts.E)));
+    TC_CUDA(cudaMemcpyAsync(e->reset_list.p, envs_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    launch_reset_list(e->ts, n, e->reset_list.p, e->stream);
+    e->launches += 1;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(e->stream));      // the host list may be reused by the caller
     return TC_OK;
 }
 

@@ -220,10 +220,11 @@ __global__ void k_pack_fields(int n, const uint16_t *__restrict__ board, const u
     for (int k = 0; k < 8; ++k) out[8 * (size_t)i + k] = w[k];
 }
 
-__global__ void k_reset(TreeStore ts, int env)
+__global__ void k_reset(TreeStore ts, int env, const int32_t *__restrict__ list)
 {
     // one block per tree: clear the hash table and the control block
-    int tree = env >= 0 ? env : (int)blockIdx.x;
+    int tree = list ? list[blockIdx.x] : (env >= 0 ? env : (int)blockIdx.x);
+    if (tree < 0 || tree >= ts.E) return;
     uint32_t *table = ts.hash + (size_t)tree * ts.hashSize;
     for (uint32_t i = threadIdx.x; i < ts.hashSize; i += blockDim.x) table[i] = 0u;
     if (threadIdx.x == 0) {
@@ -784,7 +785,12 @@ void launch_pack_fields(int n, const uint16_t *board, const uint16_t *occ, const
 
 void launch_reset(const TreeStore &ts, int env, cudaStream_t st)
 {
-    k_reset<<<env >= 0 ? 1 : ts.E, 256, 0, st>>>(ts, env);
+    k_reset<<<env >= 0 ? 1 : ts.E, 256, 0, st>>>(ts, env, nullptr);
+}
+
+void launch_reset_list(const TreeStore &ts, int n, const int32_t *envs_dev, cudaStream_t st)
+{
+    if (n > 0) k_reset<<<n, 256, 0, st>>>(ts, -1, envs_dev);
 }
 
 void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uint8_t *active_dev, cudaStream_t st)

@@ -124,6 +124,12 @@ class Engine:
     def reset(self, env=-1):
         check(self.lib.tc_reset(self.handle, int(env)))
 
+    def reset_envs(self, envs):
+        """`reset(i)` for every i in `envs` with one launch (a ply in which many games end)."""
+        envs = np.ascontiguousarray(envs, dtype=np.int32).reshape(-1)
+        if envs.size:
+            check(self.lib.tc_reset_envs(self.handle, int(envs.size), ptr(envs)))
+
     def set_roots_packed(self, states, active=None):
         states = np.ascontiguousarray(states, dtype=np.uint32).reshape(self.num_envs, 8)
         if active is not None:

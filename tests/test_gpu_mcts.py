@@ -239,3 +239,28 @@ def test_set_roots_fields_form_equals_packed_form():
     assert np.array_equal(ca, cb) and np.array_equal(a.root_q().view(np.uint64), b.root_q().view(np.uint64))
     live = tb.rules_status(roots) == 0
     assert (ca[(active == 1) & live].sum(1) == 29).all() and (ca[active == 0] == 0).all()
+
+
+def test_reset_envs_equals_per_env_resets():
+    """tc_reset_envs(list) == VectorizedMCTS.reset(i) for every i of the list (mcts.py:165-172), in one launch."""
+    n = 40
+    roots = np.zeros((n, 8), dtype=np.uint32)
+    engines = []
+    for batched in (False, True):
+        eng = tb.Engine(n, 30 * 4 + 64, hash_salt=21)
+        eng.set_roots_packed(roots)
+        eng.search(20, 2.4)
+        which = np.array([0, 3, 17, 39])
+        if batched:
+            eng.reset_envs(which)
+        else:
+            for i in which:
+                eng.reset(int(i))
+        eng.set_roots_packed(roots)
+        eng.search(10, 2.4)
+        engines.append((eng.root_counts(), eng.root_q()))
+    (c0, q0), (c1, q1) = engines
+    assert np.array_equal(c0, c1) and np.array_equal(q0.view(np.uint64), q1.view(np.uint64))
+    assert (c0[[0, 3, 17, 39]].sum(1) == 9).all() and (np.delete(c0, [0, 3, 17, 39], axis=0).sum(1) == 29).all()
+    with pytest.raises(tb._lib.TacultError):
+        tb.Engine(4, 64).reset_envs([7])
