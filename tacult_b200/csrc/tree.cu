@@ -136,28 +136,24 @@ __device__ int table_find(const TreeStore &ts, int tree, const Pos &p, uint64_t 
 #define TC_PUCT_PREFILTER 1
 #endif
 
-// per-warp view of the mutable part of TreeCtl, kept in registers during k_select
-struct Walk {
-    uint32_t n_nodes, n_edges;
-    int active, leaf_kind, leaf_node, leaf_row;
-    double leaf_value;
-    uint32_t nn_leaves, sum_leaf_legal;
-};
-
-// Creates a node for `p` (action mask am) and requests its evaluation.  Returns the node index, or -1 if a
-// pool is exhausted (error flag raised, tree parked).  off/n receive the new node's edge block.
-__device__ int create_leaf(const TreeStore &ts, int tree, Walk &w, const Pos &p, uint64_t h, uint32_t free_slot,
+// Creates a node for `p` (action mask am) and requests its evaluation.  Returns the node index, or -1 if a pool is
+// exhausted (error flag raised, tree parked).  off/n receive the new node's edge block.  Everything the rest of the
+// simulation needs (bump pointers, the leaf's row / edge block / legal mask, §8(d) counters) goes straight into the
+// control block: nothing of it is carried in registers through the descent loop (the kernel is register- and issue-bound).
+__device__ int create_leaf(const TreeStore &ts, int tree, TreeCtl *cp, const Pos &p, uint64_t h, uint32_t free_slot,
                            const uint32_t am[3], int lane, uint32_t &off, uint32_t &n)
 {
     n = (uint32_t)(__popc(am[0]) + __popc(am[1]) + __popc(am[2]));
-    if (w.n_nodes >= ts.capN || w.n_edges + n > ts.capE || free_slot == 0xFFFFFFFFu) {
-        if (lane == 0) atomicExch(ts.error_flag, 1);
-        w.active = 0;
+    const uint32_t n_nodes = cp->n_nodes, n_edges = cp->n_edges;
+    if (n_nodes >= ts.capN || n_edges + n > ts.capE || free_slot == 0xFFFFFFFFu) {
+        if (lane == 0) {
+            atomicExch(ts.error_flag, 1);
+            cp->active = 0;
+        }
         return -1;
     }
-    uint32_t idx = w.n_nodes++;
-    off = w.n_edges;
-    w.n_edges += n;
+    const uint32_t idx = n_nodes;
+    off = n_edges;
     size_t g = (size_t)tree * ts.capN + idx;
     if (lane == 0) {
         ts.node_hdr[2 * g] = make_uint4(p.mine[0], p.mine[1], p.mine[2], p.occ[0]);
@@ -174,25 +170,23 @@ __device__ int create_leaf(const TreeStore &ts, int tree, Walk &w, const Pos &p,
             rec[1] = edge_pack(0.0, 0u, (uint32_t)(lane + 32 * q));              // P (set by the expansion), coff, meta
         }
     }
-    int row = 0;
-    if (lane == 0) row = atomicAdd(ts.eval_count, 1);
-    row = __shfl_sync(FULL, row, 0);
-    if (lane == 0) {                                   // the packed position of the leaf: one 32-byte row, two vector stores
+    if (lane == 0) {
+        const int row = atomicAdd(ts.eval_count, 1);
+        // the packed position of the leaf: one 32-byte row, two vector stores
         uint4 *dst = reinterpret_cast<uint4 *>(ts.eval_state + 8 * (size_t)row);
         dst[0] = make_uint4(p.mine[0], p.mine[1], p.mine[2], p.occ[0]);
         dst[1] = make_uint4(p.occ[1], p.occ[2], p.last, 0u);
-    }
-    w.leaf_kind = LEAF_NN;
-    w.leaf_node = (int)idx;
-    w.leaf_row = row;
-    if (lane == 0) {           // what the expansion needs, straight into the control block (not carried in registers)
-        TreeCtl *cp = ts.ctl + tree;
+        cp->n_nodes = n_nodes + 1u;
+        cp->n_edges = n_edges + n;
+        cp->leaf_kind = LEAF_NN;
+        cp->leaf_node = (int)idx;
+        cp->leaf_row = row;
         cp->leaf_off = off;
         cp->leaf_n = n;
         cp->leaf_am[0] = am[0]; cp->leaf_am[1] = am[1]; cp->leaf_am[2] = am[2];
+        atomicAdd(&cp->nn_leaves, 1ull);               // reductions without a return value: one RED each
+        atomicAdd(&cp->sum_leaf_legal, (unsigned long long)n);
     }
-    w.nn_leaves += 1;
-    w.sum_leaf_legal += n;
     return (int)idx;
 }
 
@@ -350,23 +344,15 @@ __device__ __noinline__ int select_wide(const Edge *blk, uint32_t n, int lane, d
 __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree, const int lane, const double cpuct)
 {
     TreeCtl *cp = ts.ctl + tree;
-    Walk w;
-    w.active = cp->active;
-    if (!w.active) {
+    if (!cp->active) {
         if (lane == 0) { cp->leaf_kind = LEAF_NONE; cp->path_len = 0; }
         return;
     }
-    w.n_nodes = cp->n_nodes;
-    w.n_edges = cp->n_edges;
-    w.leaf_kind = LEAF_NONE;
-    w.leaf_node = -1;
-    w.leaf_row = 0;
-    w.leaf_value = 0.0;
-    w.nn_leaves = 0;
-    w.sum_leaf_legal = 0;
-    int root_idx = cp->root_idx;
-    uint32_t root_off = cp->root_off, root_n = cp->root_n;
-    uint32_t depth = 0, sum_legal = 0, terminal = 0, transp = 0;
+    // the simulation's outcome is written to the control block where it is decided (terminal leaf, new leaf, exhausted
+    // pool); until then "no leaf"
+    if (lane == 0) cp->leaf_kind = LEAF_NONE;
+    const int root_idx = cp->root_idx;
+    uint32_t depth = 0, sum_legal = 0;
     uint2 *path = ts.path + (size_t)tree * MAX_DEPTH;
     const uint4 *hdr = ts.node_hdr + 2ull * (size_t)tree * ts.capN;
 
@@ -385,10 +371,19 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
         uint64_t h = key_hash(p);
         uint32_t free_slot;
         int idx = table_find(ts, tree, p, h, lane, free_slot);
-        if (idx < 0) idx = create_leaf(ts, tree, w, p, h, free_slot, am, lane, root_off, root_n);
-        root_idx = idx;
+        uint32_t off = 0, n = 0;
+        if (idx < 0) idx = create_leaf(ts, tree, cp, p, h, free_slot, am, lane, off, n);
+        else {
+            Pos q;
+            unpack_hdr(hdr[2ull * idx], hdr[2ull * idx + 1], q, n, off);
+        }
+        if (lane == 0) {
+            cp->root_idx = idx;
+            cp->root_off = off;
+            cp->root_n = n;
+        }
     } else {
-        uint32_t off = root_off, n = root_n;
+        uint32_t off = cp->root_off, n = cp->root_n;
 #if !TC_TRACK_POS
         int cur = root_idx;
 #endif
@@ -483,8 +478,10 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             }
             sum_legal += n;
             if (best_j >= (1 << 20)) {       // cannot happen for a live position; park the tree loudly
-                if (lane == 0) atomicExch(ts.error_flag, 2);
-                w.active = 0;
+                if (lane == 0) {
+                    atomicExch(ts.error_flag, 2);
+                    cp->active = 0;
+                }
                 depth = 0;
                 break;
             }
@@ -492,10 +489,12 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             ++depth;
 
             if (child >= CHILD_TERM_BASE && child != CHILD_UNRESOLVED) {
-                int st = (int)(child - CHILD_TERM_BASE);
-                w.leaf_kind = LEAF_TERMINAL;
-                w.leaf_value = st == 2 ? 1e-4 : (st == 3 ? 1.0 : -1.0);   // utac_game.py:64-81
-                terminal += 1;
+                if (lane == 0) {
+                    const int st = (int)(child - CHILD_TERM_BASE);
+                    cp->leaf_kind = LEAF_TERMINAL;
+                    cp->leaf_value = st == 2 ? 1e-4 : (st == 3 ? 1.0 : -1.0);   // utac_game.py:64-81
+                    atomicAdd(&cp->terminal_leaves, 1ull);
+                }
                 break;
             }
             const int action = (int)(meta & 0xFFu);
@@ -522,10 +521,12 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
             int nst;
             warp_legal_mask(nx, lane, nam, nst);
             if (nst != 0) {
-                if (lane == 0) blk[best_j].child = CHILD_TERM_BASE + (uint32_t)nst;
-                w.leaf_kind = LEAF_TERMINAL;
-                w.leaf_value = nst == 2 ? 1e-4 : (nst == 3 ? 1.0 : -1.0);
-                terminal += 1;
+                if (lane == 0) {
+                    blk[best_j].child = CHILD_TERM_BASE + (uint32_t)nst;
+                    cp->leaf_kind = LEAF_TERMINAL;
+                    cp->leaf_value = nst == 2 ? 1e-4 : (nst == 3 ? 1.0 : -1.0);
+                    atomicAdd(&cp->terminal_leaves, 1ull);
+                }
                 break;
             }
             uint64_t h = key_hash(nx);
@@ -539,8 +540,8 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
                     blk[best_j].child = (uint32_t)idx;
                     blk[best_j].coff = co;
                     blk[best_j].meta = (uint32_t)action | (cn << 8);
+                    atomicAdd(&cp->transpositions, 1ull);
                 }
-                transp += 1;
 #if TC_TRACK_POS
                 p = nx;
 #else
@@ -551,7 +552,7 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
                 continue;
             }
             uint32_t co = 0, cn = 0;
-            idx = create_leaf(ts, tree, w, nx, h, free_slot, nam, lane, co, cn);
+            idx = create_leaf(ts, tree, cp, nx, h, free_slot, nam, lane, co, cn);
             if (idx >= 0) {
                 if (lane == 0) {
                     blk[best_j].child = (uint32_t)idx;
@@ -559,34 +560,17 @@ __device__ __forceinline__ void select_tree(const TreeStore &ts, const int tree,
                     blk[best_j].meta = (uint32_t)action | (cn << 8);
                 }
             } else {
-                depth = 0;              // pool exhausted: drop this simulation
-                w.leaf_kind = LEAF_NONE;
+                depth = 0;              // pool exhausted: drop this simulation (leaf_kind stays LEAF_NONE)
             }
             break;
         }
     }
     if (lane == 0) {
-        cp->root_idx = root_idx;
-        cp->root_off = root_off;
-        cp->root_n = root_n;
-        cp->active = w.active;
-        cp->n_nodes = w.n_nodes;
-        cp->n_edges = w.n_edges;
-        cp->leaf_kind = w.leaf_kind;
-        cp->leaf_node = w.leaf_node;
-        cp->leaf_row = w.leaf_row;
-        cp->leaf_value = w.leaf_value;
         cp->path_len = (int)depth;
         // §8(d) counters: reductions without a return value (one RED each, no load on the warp's critical path)
         atomicAdd(&cp->sims, 1ull);
         atomicAdd(&cp->sum_depth, (unsigned long long)depth);
         atomicAdd(&cp->sum_legal, (unsigned long long)sum_legal);
-        if (w.nn_leaves) {
-            atomicAdd(&cp->nn_leaves, (unsigned long long)w.nn_leaves);
-            atomicAdd(&cp->sum_leaf_legal, (unsigned long long)w.sum_leaf_legal);
-        }
-        if (terminal) atomicAdd(&cp->terminal_leaves, (unsigned long long)terminal);
-        if (transp) atomicAdd(&cp->transpositions, (unsigned long long)transp);
     }
 }
 
