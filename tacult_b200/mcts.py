@@ -97,16 +97,18 @@ class VectorizedMCTS:
         self.engine.set_roots_packed(states, active)
         self.engine.search(1, float(self.args.cpuct))
 
-    def rootCounts(self, canonicalBoards):
-        """`numMCTSSims` simulations, then the root edge visit counts (the `_counts` of mcts.py:191-198)."""
+    def _root_counts_u32(self, canonicalBoards):
         states, active = pack_gamestates(canonicalBoards)
         self.engine.set_roots_packed(states, active)
         self.engine.search(int(self.args.numMCTSSims), float(self.args.cpuct))
-        return self.engine.root_counts(out=self._counts.array).astype(np.int64)
+        return self.engine.root_counts(out=self._counts.array)        # a view of the pinned staging buffer
+
+    def rootCounts(self, canonicalBoards):
+        """`numMCTSSims` simulations, then the root edge visit counts (the `_counts` of mcts.py:191-198)."""
+        return self._root_counts_u32(canonicalBoards).astype(np.int64)
 
     def getActionProbs(self, canonicalBoards, temps):     # mcts.py:175-214
-        counts_all = self.rootCounts(canonicalBoards)
-        return action_probs_from_counts(counts_all, temps)
+        return action_probs_from_counts(self._root_counts_u32(canonicalBoards), temps)
 
 
 def action_probs_from_counts(counts_all, temps):
