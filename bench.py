@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--sims", type=int, default=200)
-    ap.add_argument("--evaluator", default="auto", choices=["auto", "f32", "bf16"])
+    ap.add_argument("--evaluator", default="auto", choices=["auto", "f32", "bf16", "bf16_masked"],
+                    help="bf16_masked = production mode (masked soft-max in the heads kernel); not the parity-mode headline")
     ap.add_argument("--stagger-plies", type=int, default=150)
     ap.add_argument("--profile-plies", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -302,7 +303,7 @@ def run_b200(a):
             evaluator = "bf16"
         except tb._lib.TacultError:
             evaluator = "f32"
-    eng.set_evaluator(tb._lib.EVAL_NET_BF16 if evaluator == "bf16" else tb._lib.EVAL_NET_F32)
+    eng.set_evaluator({"bf16": tb._lib.EVAL_NET_BF16, "bf16_masked": tb._lib.EVAL_NET_BF16_MASKED}.get(evaluator, tb._lib.EVAL_NET_F32))
 
     # ---- device-resident self-play: the headline `value` --------------------------------------
     seed = 1000 + rank
