@@ -165,6 +165,14 @@ int tc_set_evaluator(tc_engine *e, int evaluator);
 int tc_set_roots(tc_engine *e, const uint16_t *board_host, const uint16_t *occ_host,
                  const int8_t *last_square_host, const uint8_t *active_host);
 int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, const uint8_t *active_host);
+/* One ply for every env on the device: the env's root (as last set by tc_set_roots* or tc_advance) + actions[i] -> the
+ * canonical successor (getNextState + getCanonicalForm, utac_game.py:34-47,83-107), which becomes the root of the next
+ * tc_search; the tree and its statistics are kept, as the reference's dicts are across plies (coach.py:162).
+ * actions[i] < 0 leaves env i where it is.  restart != 0: an env whose game just ended gets a fresh tree and the initial
+ * position (VectorizedMCTS.reset(i) mcts.py:165-172 + getInitBoard), otherwise it idles.  states_host / status_host
+ * (optional): the successors and their TC_* status as seen by their side to move, before any restart.
+ * An illegal action -> TC_EILLEGAL (that env keeps its position). */
+int tc_advance(tc_engine *e, const int8_t *actions_host, int restart, uint32_t *states_host, int8_t *status_host);
 /* num_sims x VectorizedMCTS.search (mcts.py:184-185,217-342); cpuct read per call like args.cpuct (mcts.py:309) */
 int tc_search(tc_engine *e, int num_sims, double cpuct);
 /* root edge visit counts, the `_counts` of getActionProbs (mcts.py:191-198): counts[i][a] */

@@ -146,6 +146,7 @@ SYMBOLS = {
     "tc_set_evaluator": (_i, [_vp, _i]),
     "tc_set_roots": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "tc_set_roots_packed": (_i, [_vp, _vp, _vp]),
+    "tc_advance": (_i, [_vp, _vp, _i, _vp, _vp]),
     "tc_search": (_i, [_vp, _i, _d]),
     "tc_root_counts": (_i, [_vp, _vp]),
     "tc_root_q": (_i, [_vp, _vp]),

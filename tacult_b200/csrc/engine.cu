@@ -86,6 +86,8 @@ struct tc_engine {
     DevBuf<int8_t> fld_last;
     DevBuf<double> root_q;
     DevBuf<int32_t> reset_list;
+    DevBuf<int8_t> adv_actions, adv_status;
+    DevBuf<int> adv_illegal;
     // evaluation log
     DevBuf<uint32_t> log_states;
     DevBuf<float> log_pi, log_v;
@@ -414,6 +416,31 @@ extern "C" int tc_set_roots_packed(tc_engine *e, const uint32_t *states_host, co
     TC_CUDA(cudaMemcpyAsync(e->root_states.p, states_host, 8 * (size_t)e->ts.E * sizeof(uint32_t),
                             cudaMemcpyHostToDevice, e->stream));
     return set_roots_dev(e, active_host);
+}
+
+extern "C" int tc_advance(tc_engine *e, const int8_t *actions_host, int restart, uint32_t *states_host, int8_t *status_host)
+{
+    TC_TRY(check_engine(e));
+    TC_CHECK(actions_host, TC_EINVAL, "tc_advance: null actions");
+    const size_t E = (size_t)e->ts.E;
+    if (e->adv_status.n < E) {
+        TC_CUDA(e->adv_actions.alloc(E));
+        TC_CUDA(e->adv_status.alloc(E));
+        TC_CUDA(e->adv_illegal.alloc(1));
+    }
+    TC_CUDA(cudaMemcpyAsync(e->adv_actions.p, actions_host, E, cudaMemcpyHostToDevice, e->stream));
+    TC_CUDA(cudaMemsetAsync(e->adv_illegal.p, 0, sizeof(int), e->stream));
+    launch_advance(e->ts, e->adv_actions.p, restart, e->root_states.p, e->adv_status.p, e->adv_illegal.p, e->stream);
+    e->launches += 1;
+    TC_CUDA(cudaGetLastError());
+    int bad = 0;
+    if (states_host)
+        TC_CUDA(cudaMemcpyAsync(states_host, e->root_states.p, 32 * E, cudaMemcpyDeviceToHost, e->stream));
+    if (status_host) TC_CUDA(cudaMemcpyAsync(status_host, e->adv_status.p, E, cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaMemcpyAsync(&bad, e->adv_illegal.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    TC_CUDA(cudaStreamSynchronize(e->stream));
+    TC_CHECK(bad == 0, TC_EILLEGAL, "tc_advance: %d illegal move(s) requested", bad);
+    return TC_OK;
 }
 
 // One lock-step simulation for every tree of part `h`: select -> evaluate leaves -> expand + backup.

@@ -275,6 +275,76 @@ __global__ void k_set_roots(TreeStore ts, const uint32_t *__restrict__ states, c
     }
 }
 
+// One ply for every env on the device (tc_advance): the stored root + the chosen action -> canonical successor, which is
+// looked up in the tree (statistics persist across plies, coach.py:162) and becomes the next root.  A finished game
+// either parks the env or, with `restart`, gets a fresh tree and the initial position (mcts.py:165-172 + getInitBoard).
+__global__ void k_advance(TreeStore ts, const int8_t *__restrict__ actions, int restart, uint32_t *__restrict__ states_out,
+                          int8_t *__restrict__ status_out, int *__restrict__ illegal)
+{
+    const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tree >= ts.E) return;
+    TreeCtl *c = ts.ctl + tree;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = c->root_state[k];
+    Pos p = unpack(w);
+    const int a = actions[tree];
+    int status = status_of(summarize(p));
+    if (a >= 0) {
+        uint32_t lw[3];
+        legal_words(p, summarize(p), lw);
+        if (a > 80 || !action_bit(lw, a)) {
+            if (lane == 0) atomicAdd(illegal, 1);
+        } else {
+            p = play(p, a);
+            status = status_of(summarize(p));
+        }
+    }
+    if (lane == 0) {
+        pack(p, w);
+        if (states_out) {
+            uint4 *dst = reinterpret_cast<uint4 *>(states_out + 8 * (size_t)tree);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        if (status_out) status_out[tree] = (int8_t)status;
+    }
+    const bool fresh = status != 0 && restart != 0;
+    if (fresh) {                                   // new game: empty tree, initial position
+        uint32_t *table = ts.hash + (size_t)tree * ts.hashSize;
+        for (uint32_t i = lane; i < ts.hashSize; i += 32) table[i] = 0u;
+        p.mine[0] = p.mine[1] = p.mine[2] = p.occ[0] = p.occ[1] = p.occ[2] = 0u;
+        p.last = 0u;
+    }
+    const bool on = fresh || status == 0;
+    uint32_t free_slot, off = 0, n = 0;
+    int idx = -1;
+    if (on && !fresh) {
+        idx = table_find(ts, tree, p, key_hash(p), lane, free_slot);
+        if (idx >= 0) {
+            const uint4 *hdr = ts.node_hdr + 2ull * ((size_t)tree * ts.capN + idx);
+            Pos q;
+            unpack_hdr(hdr[0], hdr[1], q, n, off);
+        }
+    }
+    if (lane == 0) {
+        pack(p, w);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c->root_state[k] = w[k];
+        c->root_idx = idx;
+        c->root_off = off;
+        c->root_n = n;
+        c->active = on ? 1 : 0;
+        c->leaf_kind = LEAF_NONE;
+        c->path_len = 0;
+        if (fresh) {
+            c->n_nodes = 0;
+            c->n_edges = 0;
+        }
+    }
+}
+
 // Order-preserving map of a double to an unsigned key (-0.0 folded into +0.0 first, so equal values give equal keys
 // exactly as the reference's strict '>' sees them).
 __device__ __forceinline__ unsigned long long double_key(double u)
@@ -780,6 +850,12 @@ void launch_reset_list(const TreeStore &ts, int n, const int32_t *envs_dev, cuda
 void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uint8_t *active_dev, cudaStream_t st)
 {
     k_set_roots<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, states_dev, active_dev);
+}
+
+void launch_advance(const TreeStore &ts, const int8_t *actions_dev, int restart, uint32_t *states_dev, int8_t *status_dev,
+                    int *illegal_dev, cudaStream_t st)
+{
+    k_advance<<<warp_grid(ts.E, 128), 128, 0, st>>>(ts, actions_dev, restart, states_dev, status_dev, illegal_dev);
 }
 
 void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st)

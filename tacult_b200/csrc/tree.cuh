@@ -110,6 +110,8 @@ struct HashEvalParams {
 void launch_set_roots(const TreeStore &ts, const uint32_t *states_dev, const uint8_t *active_dev, cudaStream_t st);
 void launch_reset(const TreeStore &ts, int env, cudaStream_t st);
 void launch_reset_list(const TreeStore &ts, int n, const int32_t *envs_dev, cudaStream_t st);
+void launch_advance(const TreeStore &ts, const int8_t *actions_dev, int restart, uint32_t *states_dev, int8_t *status_dev,
+                    int *illegal_dev, cudaStream_t st);
 void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st);
 void launch_expand_backup(const TreeStore &ts, cudaStream_t st);
 void launch_backup_select(const TreeStore &ts, double cpuct, cudaStream_t st);

@@ -144,6 +144,17 @@ class Engine:
             active = np.ascontiguousarray(active, dtype=np.uint8).reshape(self.num_envs)
         check(self.lib.tc_set_roots(self.handle, ptr(board), ptr(occ), ptr(last), ptr(active)))
 
+    def advance(self, actions, restart=False, states_out=None, status_out=None):
+        """One ply on the device (tc_advance): every env's root + its action -> the next root, trees kept; finished games
+        restart with a fresh tree when `restart`.  Returns (successor positions u32[E,8], status i8[E])."""
+        actions = np.ascontiguousarray(actions, dtype=np.int8).reshape(self.num_envs)
+        if states_out is None:
+            states_out = np.empty((self.num_envs, 8), dtype=np.uint32)
+        if status_out is None:
+            status_out = np.empty(self.num_envs, dtype=np.int8)
+        check(self.lib.tc_advance(self.handle, ptr(actions), int(bool(restart)), ptr(states_out), ptr(status_out)))
+        return states_out, status_out
+
     def search(self, num_sims, cpuct):
         check(self.lib.tc_search(self.handle, int(num_sims), float(cpuct)))
 

@@ -264,3 +264,43 @@ def test_reset_envs_equals_per_env_resets():
     assert (c0[[0, 3, 17, 39]].sum(1) == 9).all() and (np.delete(c0, [0, 3, 17, 39], axis=0).sum(1) == 29).all()
     with pytest.raises(tb._lib.TacultError):
         tb.Engine(4, 64).reset_envs([7])
+
+
+def test_advance_on_device_equals_host_stepping():
+    """tc_advance (root + action -> next root on the device, trees kept, finished games restarted) against the host-driven
+    sequence it replaces: tc_rules_step + tc_reset_envs + tc_set_roots_packed.  Same visit counts and Q at every ply."""
+    n, sims = 96, 24
+    rng = np.random.RandomState(5)
+    a = tb.Engine(n, sims * 82 + 64, hash_salt=33)
+    b = tb.Engine(n, sims * 82 + 64, hash_salt=33)
+    states = np.zeros((n, 8), dtype=np.uint32)
+    a.set_roots_packed(states)
+    b.set_roots_packed(states)
+    finished = 0
+    for ply in range(60):
+        a.search(sims, 2.4)
+        b.search(sims, 2.4)
+        ca, cb = a.root_counts(), b.root_counts()
+        assert np.array_equal(ca, cb) and np.array_equal(a.root_q().view(np.uint64), b.root_q().view(np.uint64)), ply
+        acts = np.array([rng.choice(np.flatnonzero(c)) for c in ca], dtype=np.int8)
+        # host path
+        nxt, st = tb.rules_step(states, acts)
+        done = np.flatnonzero(st != 0)
+        nxt[done] = 0
+        a.reset_envs(done)
+        a.set_roots_packed(nxt)
+        # device path
+        got, gst = b.advance(acts, restart=True)
+        assert np.array_equal(gst, st)
+        live = st == 0
+        assert np.array_equal(got[live], nxt[live])
+        states = nxt
+        finished += len(done)
+    assert finished >= 3                       # restarts were exercised
+    # an illegal action is refused loudly and leaves that env alone
+    bad = np.full(n, -1, dtype=np.int8)
+    occupied = int(np.flatnonzero(tb.rules_legal_mask(states[:1])[0] == 0)[0])
+    bad[0] = occupied
+    with pytest.raises(tb._lib.TacultError) as err:
+        b.advance(bad)
+    assert err.value.code == tb._lib.TC_EILLEGAL
