@@ -36,6 +36,12 @@ def stage():
         manifest[rel] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
     with open(os.path.join(DEST, "MANIFEST.json"), "w") as fh:
         json.dump({"source": SOURCE, "sha256": manifest}, fh, indent=1)
+    with open(os.path.join(DEST, "README.txt"), "w") as fh:
+        fh.write("BUILD OUTPUT, NOT REPOSITORY SOURCE (git-ignored).\n"
+                 "Byte-for-byte staging of the reference's hot-path modules by oracle/stage_reference.py, run from\n"
+                 "__graft_entry__.build() where /root/reference exists, so that `bench.py --impl reference` and the\n"
+                 "`cpu_baseline` leg can time the UNMODIFIED reference on the GPU box.  Nothing under tacult_b200/ reads\n"
+                 "this directory; tests only use it for the drop-in check (tests/dropin_reference_coach.py).\n")
     return True
 
 
