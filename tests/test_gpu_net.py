@@ -84,3 +84,22 @@ def test_load_errors():
     with pytest.raises(tb._lib.TacultError) as err:
         eng.forward(np.zeros((1, 4, 9, 9), dtype=np.float32))
     assert err.value.code == tb._lib.TC_ESTATE
+
+
+def test_plane_order_on_the_device():
+    """A checkpoint trained on another ordering of the input planes: load_weights(plane_order=...) must give what the
+    original network gives when it is fed the planes in ITS order."""
+    import resnet_oracle
+    sd = resnet_oracle.make_state_dict(9, 16, 2, 64)
+    order = (2, 0, 3, 1)                    # the net's plane i is the engine's plane order[i]
+    res = tb.rules_playouts(8, 0, 64, max_plies=30)
+    states = np.array([list(r.final_state) for r in res], dtype=np.uint32)
+    obs = tb.rules_encode_obs(states)       # engine order
+    eng = tb.Engine(64, 2)
+    eng.load_weights(sd, plane_order=order)
+    pi, v = eng.forward_states(states)
+    rpi, rv = resnet_oracle.forward(sd, obs[:, list(order)])
+    assert np.abs(pi - rpi.numpy()).max() < 1e-3 and np.abs(v - rv.numpy().ravel()).max() < 1e-3
+    eng.load_weights(sd)
+    pi0, _ = eng.forward_states(states)
+    assert np.abs(pi0 - pi).max() > 1e-4    # and the permutation does matter
