@@ -541,6 +541,10 @@ struct NetBF16Impl {
     // fused shared-memory-resident trunk (C <= 64)
     bool fused = false;
     int fused_G = 0, fused_T = 0;
+    // column-tiled fused trunk (C == 32): weights as [layer][ky][3C x K] blocks
+    bool col = false;
+    DevBuf<__nv_bfloat16> col_w_stem, col_w_conv;
+    CUtensorMap map_col_stem, map_col_conv;
     DevBuf<__nv_bfloat16> conv_w_all;      // [n_conv][9][C][C]
     DevBuf<__nv_bfloat16> bias_tiles;      // [1 + n_conv][C][16]: bias as a K-major UMMA operand (hi, lo, 0...)
     CUtensorMap map_conv_w_all, map_bias_tiles;
@@ -734,6 +738,17 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
             TC_TRY(upload(m.bias_tiles, btiles));
             TC_TRY(make_map(&m.map_bias_tiles, m.bias_tiles.p, (uint64_t)(1 + L) * C, 16, (uint32_t)C, 16));
             TC_TRY(make_map(&m.map_conv_w_all, m.conv_w_all.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)C, (uint32_t)C));
+            const char *cz = getenv("TACULT_TRUNK_COL");
+            m.col = trunk_col_supported(C, I) && !share_sm && (!cz || atoi(cz) != 0);
+            if (m.col) {
+                std::vector<__nv_bfloat16> ws((size_t)9 * C * 16), wc(std::max<size_t>(1, L) * 9 * C * C, __float2bfloat16_rn(0.f));
+                trunk_col_pack(f.stem_w.data(), C, I, 16, ws.data());
+                for (size_t l = 0; l < L; ++l) trunk_col_pack(f.conv_w[l].data(), C, C, C, wc.data() + l * 9 * C * C);
+                TC_TRY(upload(m.col_w_stem, ws));
+                TC_TRY(upload(m.col_w_conv, wc));
+                TC_TRY(make_map(&m.map_col_stem, m.col_w_stem.p, (uint64_t)9 * C, 16, (uint32_t)(3 * C), 16));
+                TC_TRY(make_map(&m.map_col_conv, m.col_w_conv.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)(3 * C), (uint32_t)C));
+            }
         }
     }
     const size_t budget = 200 * 1024;
@@ -798,8 +813,12 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
     const int total = 2 * m.d.num_residual_blocks;
     if (m.fused && to_flat && n_convs >= total) {
         prof->begin(TC_K_NN_CONV, st);
-        launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.map_bias_tiles, m.fused_G, m.fused_T, total, I, batch,
-                           count_dev, states, obs, m.flat.p, m.sm_count, st);
+        if (m.col)
+            launch_trunk_col(m.map_col_stem, m.map_col_conv, m.map_bias_tiles, total, I, batch, count_dev, states, obs, m.flat.p,
+                             m.sm_count, st);
+        else
+            launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.map_bias_tiles, m.fused_G, m.fused_T, total, I, batch,
+                               count_dev, states, obs, m.flat.p, m.sm_count, st);
         prof->end(st);
         ++launches;
         return -1;

@@ -1,0 +1,491 @@
+// Column-tiled fused trunk for the 32-channel net: conv_in and every residual-block convolution of `_UtacNNet`
+// (/root/reference/src/tacult/network.py:84-89, ResidualBlock 35-41) in one kernel, like k_trunk_fused (nn_fused.cu),
+// but with HALF the shared-memory operand traffic per position and layer - the quantity that bounds a 32-channel
+// implicit GEMM on this machine (a UMMA costs (4096 + 32 N) / 128 cycles of operand fetch).
+//
+// Layout.  A pass holds up to 12 positions.  UMMA tile j (j = 0..8) is BOARD COLUMN j of all of them: lane 10 g + r of
+// the tile is cell (row r, column j) of position g, lane 10 g + 9 a zero pad row shared by positions g and g + 1, lanes
+// 120..127 spare (zero).  With that layout
+//   * a vertical tap (dy) is the same shared-memory tile read through a descriptor moved by dy rows, as before;
+//   * a horizontal tap (dx) is ANOTHER TILE, SAME LANE.  So the three dx taps are stacked in N: the UMMA of input tile
+//     i and kernel row dy multiplies the activations by the [3C x C] block (W[dy][dx=+1] | W[dy][0] | W[dy][dx=-1])
+//     and accumulates into the 96 TMEM columns that hold output tiles i-1, i, i+1 side by side.  The sums over dx
+//     happen in the accumulators; no lane ever needs another lane's value, and the epilogue is the old one
+//     (one tcgen05.ld, ReLU, pack, store).
+// Per tile and layer: 6 UMMAs of N = 96 (56 cycles each) instead of 18 of N = 32 (40 each); 31 KB of operands per
+// position and layer instead of 78 KB.  Accumulators: 11 blocks of 32 columns (out tiles -1 and 9 are dummies that
+// catch the edge tiles' outer blocks).
+//
+// One thread issues every UMMA, in a fixed order: accumulating UMMAs of one thread into the same columns run
+// back to back (56 cycles per N = 96 UMMA, measured: tools/probes/umma_issue_probe.cu) and the summation order is
+// the same in every run, whereas two threads accumulating into overlapping columns serialise at ~250 cycles.  The
+// issue loop is straight-line code per tile: a rolled loop re-uses the uniform registers that carry the descriptors and
+// drops to 69 cycles per UMMA (same probe).  Bias = ones x bias tile (N = 32, overwrite) into each output block before
+// its first conv UMMA; residual = identity-tile UMMAs into the centre block.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "nn_bf16.cuh"
+#include "nn_fused.cuh"
+#include "rules.cuh"
+#include "rules_warp.cuh"
+#include "tcgen05.cuh"
+
+#ifndef TC_COL_TILE_UNROLL
+#define TC_COL_TILE_UNROLL 9
+#endif
+
+namespace tc {
+
+namespace col {
+
+constexpr int C = 32;
+constexpr int SW = 2 * C;                // activation row = one swizzle span
+constexpr int N3 = 3 * C;
+constexpr int TILES = 9;                 // board columns
+constexpr int PITCH = 10;                // lanes per position: 9 board rows + 1 zero row
+constexpr int GMAX = 128 / PITCH;        // 12 positions per pass
+constexpr int FIRST_EPI = 4;             // warp 0: TMA, warp 1: UMMA issue, warps 2-3: plane encoding only
+constexpr int EPI_WARPS = 8;             // two per TMEM lane quarter
+constexpr int THREADS = 32 * (FIRST_EPI + EPI_WARPS);
+constexpr int LEAD = 16, TAIL = 16;      // zero rows around the nine tiles (1 KB each: tiles stay 1024-aligned)
+constexpr int BUF_BYTES = (LEAD + 128 * TILES + TAIL) * SW;
+constexpr int W_DY = N3 * SW;            // one kernel row of a conv layer: [3C x C] bf16, K-major, 64-byte swizzle
+constexpr int WS_DY = N3 * 32;           // one kernel row of the stem:     [3C x 16]
+constexpr int W_BUF = 3 * W_DY + 1024;   // + bias tile [C x 16]
+constexpr int BAR_STRIDE = 16;
+constexpr int TILE_UNROLL = TC_COL_TILE_UNROLL;   // tiles of a layer issued as straight-line code
+
+struct Params {
+    const int *count_dev;
+    int batch;
+    int n_conv;              // 2 * residual blocks
+    int in_planes;
+    const uint32_t *states;  // packed positions, or
+    const float *obs;        // dense planes [row][in_planes][81]
+    __nv_bfloat16 *out;      // compact [row][81][C] (fc1 input)
+    long long *timeline;     // optional clock64 marks of CTA 0
+    int pdl_trigger;
+    int dbg;                 // TACULT_COL_DBG bits (timing experiments only; results are wrong): 1 no bias, 2 no residual
+};
+
+__device__ __forceinline__ uint32_t swz(uint32_t off)       // byte offset inside a 1024-aligned buffer -> swizzled
+{
+    return off ^ (((off >> 7) & (uint32_t)(SW / 16 - 1)) << 4);
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits, __nv_bfloat162 zero2)
+{
+    __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(__uint_as_float(a_bits), __uint_as_float(b_bits)), zero2);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <int SWB>
+__device__ __forceinline__ uint64_t desc_of(uint32_t saddr)
+{
+    constexpr uint32_t layout = SWB == 128 ? 2u : (SWB == 64 ? 4u : 6u);
+    constexpr uint32_t hi = ((8u * SWB) >> 4) | (1u << 14) | (layout << 29);
+    return ((uint64_t)hi << 32) | (uint64_t)(saddr >> 4);
+}
+
+// Offsets of the shared-memory carve-up from its 1024-aligned base: compile-time constants, so that every UMMA
+// descriptor of the issue loop is (uniform base + constant) and is built in the uniform datapath.  A descriptor that
+// travels through a vector register costs an R2UR, and those were measured at ~35 cycles each in the issuing thread:
+// 7 per tile made a tile cost 620 cycles instead of the 340-480 of its UMMAs (tools/probes/umma_issue_probe.cu).
+constexpr uint32_t X_OFF = 0, Y_OFF = BUF_BYTES, W_OFF = 2 * BUF_BYTES;
+constexpr uint32_t ID_OFF = W_OFF + 2 * W_BUF, ONES_OFF = ID_OFF + C * SW, BARS_OFF = ONES_OFF + 4096;
+
+// low word of a descriptor: (address >> 4); the base is 1024-aligned, so the shift distributes
+template <int SWB>
+__device__ __forceinline__ uint64_t desc_at(uint32_t base4, uint32_t off)
+{
+    constexpr uint32_t layout = SWB == 128 ? 2u : (SWB == 64 ? 4u : 6u);
+    constexpr uint32_t hi = ((8u * SWB) >> 4) | (1u << 14) | (layout << 29);
+    return ((uint64_t)hi << 32) | (uint64_t)(base4 + (off >> 4));
+}
+
+// Every UMMA of one layer, issued by one thread in a fixed order.  KIND 0: stem (planes in Y -> X), 1: first conv of a
+// block (X -> Y), 2: second conv (Y -> X, + residual X).  WB: weight buffer.  Input tile i accumulates into the blocks
+// of output tiles i-1, i, i+1; output tile j is complete (tdone[j]) once input tile j+1 has been issued.
+template <int KIND, int WB>
+__device__ __forceinline__ void issue_layer(uint32_t base4, uint32_t tmem_base, uint64_t *tdone, uint64_t *prev, uint32_t pph,
+                                            uint64_t *wfree_bar, int dbg)
+{
+    constexpr uint32_t SRC = KIND == 1 ? X_OFF : Y_OFF;
+    constexpr uint32_t WL = W_OFF + WB * W_BUF;
+    const uint32_t idesc96 = make_instr_desc(N3), idesc32 = make_instr_desc(C);
+    const uint64_t ones_desc = desc_at<32>(base4, ONES_OFF), bias_desc = desc_at<32>(base4, WL + 3 * W_DY);
+#pragma unroll(TILE_UNROLL)
+    for (int i = 0; i < TILES; ++i) {
+        if (KIND != 0) {
+            if (i == 0) mbar_wait(prev, pph);
+            if (i + 1 < TILES) mbar_wait(prev + i + 1, pph);
+            tc_fence_after();
+        }
+        const uint32_t d = tmem_base + (uint32_t)(C * i);
+        if (!(dbg & 1)) {
+            if (i == 0) umma_bf16(d + C, ones_desc, bias_desc, idesc32, 0u);
+            if (i + 1 < TILES) umma_bf16(d + 2 * C, ones_desc, bias_desc, idesc32, 0u);
+        }
+        constexpr uint32_t TILE0 = (uint32_t)(LEAD * SW);
+        const uint32_t tile = TILE0 + (uint32_t)(128 * SW * i);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t a = SRC + tile + (uint32_t)(dy * SW) - (uint32_t)SW;
+            if (KIND == 0) {
+                umma_bf16(d, desc_at<SW>(base4, a), desc_at<32>(base4, WL + (uint32_t)(dy * W_DY)), idesc96, 1u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < C / 16; ++k)
+                    umma_bf16(d, desc_at<SW>(base4, a + 32u * k), desc_at<SW>(base4, WL + (uint32_t)(dy * W_DY) + 32u * k), idesc96, 1u);
+            }
+        }
+        if (KIND == 2 && !(dbg & 2)) {
+#pragma unroll
+            for (int k = 0; k < C / 16; ++k)
+                umma_bf16(d + C, desc_at<SW>(base4, X_OFF + tile + 32u * k), desc_at<SW>(base4, ID_OFF + 32u * k), idesc32, 1u);
+        }
+        if (i >= 1) umma_commit(tdone + i - 1);
+    }
+    umma_commit(tdone + TILES - 1);
+    umma_commit(wfree_bar);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant__ CUtensorMap tmW_stem,
+                                                          const __grid_constant__ CUtensorMap tmW_conv,
+                                                          const __grid_constant__ CUtensorMap tmBias, Params P)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *X = smem + X_OFF, *Y = smem + Y_OFF;
+    uint8_t *W = smem + W_OFF;                                  // two layers' weights: layer n lives in buffer n & 1
+    uint8_t *Id = smem + ID_OFF;                                // identity [C x C]
+    uint8_t *Ones = smem + ONES_OFF;                            // 128 rows x 16 ones
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + BARS_OFF);
+    uint64_t *tdone = bars;                                     // [j]: every UMMA into output tile j has completed
+    uint64_t *aready = bars + BAR_STRIDE;                       // [layer & 1][j]: output tile j drained and written
+    uint64_t *wfull = bars + 3 * BAR_STRIDE, *wfree = wfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfree + 2);
+    uint32_t *ptab = tmem_slot + 4;                             // [GMAX][12]: stones of the mover, all stones, legal cells
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_layers = 1 + P.n_conv;
+
+    // ---- prologue that depends on nothing the previous kernel wrote (programmatic dependent launch, common.cuh) ----
+    griddep_launch(P.pdl_trigger == 1);
+    long long *marks = (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? P.timeline : nullptr;
+    if (marks) marks[0] = clock64();
+    long long *marks2 = (P.timeline && blockIdx.x == 0) ? P.timeline : nullptr;      // any thread of CTA 0
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW_stem);
+        tma_prefetch_desc(&tmW_conv);
+        tma_prefetch_desc(&tmBias);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    // pad rows and spare lanes of both activation buffers must read as zero for ever: clear everything once
+    for (int i = threadIdx.x; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < C * SW / 16; i += THREADS) reinterpret_cast<uint4 *>(Id)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 4096 / 16; i += THREADS)
+        reinterpret_cast<uint4 *>(Ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+
+    // ---- from here on the leaf count and the leaf positions written by the descent kernel are read ----
+    if (marks) marks[1] = clock64();
+    griddep_wait();
+    if (marks) marks[2] = clock64();
+    int count = P.batch;
+    if (P.count_dev) count = min(count, *P.count_dev);
+    const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int p_begin = min(count, (int)blockIdx.x * per), p_end = min(count, p_begin + per);
+    const int n_pass = (p_end - p_begin + GMAX - 1) / GMAX;
+    if (n_pass == 0 && threadIdx.x == 0) griddep_launch(P.pdl_trigger == 2);
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < TILES; ++j) mbar_init(tdone + j, 1);
+        for (int b = 0; b < 2; ++b)
+            for (int j = 0; j < TILES; ++j) mbar_init(aready + b * BAR_STRIDE + j, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, 1); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x < C)            // identity, K-major rows of SW bytes in the swizzle pattern
+        *reinterpret_cast<__nv_bfloat16 *>(Id + swz((uint32_t)threadIdx.x * SW + (uint32_t)threadIdx.x * 2u)) = __float2bfloat16_rn(1.f);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
+
+    uint32_t lcount = 0;       // layers executed so far by this CTA (mbarrier phase = lcount & 1)
+    if (warp == 0 && lane == 0 && n_pass > 0) {
+        mbar_expect_tx(wfull, 3u * WS_DY + C * 32u);
+        for (int dy = 0; dy < 3; ++dy) tma_load_2d(W + dy * W_DY, &tmW_stem, wfull, 0, dy * N3);
+        tma_load_2d(W + 3 * W_DY, &tmBias, wfull, 0, 0);
+    }
+
+    const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y);
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int pos0 = p_begin + pass * GMAX;
+        const int G = min(GMAX, p_end - pos0);
+        // ---- observation planes of the pass -> channels 0..15 of the rows in Y (pad rows are never touched).  The legal
+        //      mask of a position is computed ONCE, by a warp (rules_warp.cuh), not once per cell: per-cell scalar
+        //      rules made this phase 8.7 k cycles per pass, a fifth of the kernel ----
+        if (P.states) {
+            for (int g = warp; g < G; g += THREADS / 32) {
+                const uint32_t w = lane < 8 ? P.states[8 * (size_t)(pos0 + g) + lane] : 0u;
+                uint32_t wd[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wd[k] = __shfl_sync(0xFFFFFFFFu, w, k);
+                const Pos p = unpack(wd);
+                uint32_t am[3], mm[3], oo[3];
+                int status;
+                warp_legal_mask<true>(p, lane, am, status, mm, oo);
+                if (lane < 3) {
+                    ptab[g * 12 + lane] = mm[lane];
+                    ptab[g * 12 + 3 + lane] = oo[lane];
+                    ptab[g * 12 + 6 + lane] = am[lane];
+                }
+            }
+            __syncthreads();
+        }
+        // consecutive threads write consecutive rows of one tile (64 bytes apart: conflict-free 16-byte stores); cells of
+        // one board row live 8 KB apart and would all fall on the same banks
+        for (int idx = threadIdx.x; idx < G * 81; idx += THREADS) {
+            const int cc = idx / (9 * G), gr = idx - 9 * G * cc;
+            const int g = gr / 9, r = gr - 9 * g;
+            const int a = 9 * r + cc;
+            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = make_uint4(0u, 0u, 0u, 0u);
+            if (P.states) {
+                const uint32_t *t = ptab + g * 12 + (a >> 5);
+                const uint32_t bit = 1u << (a & 31);
+                const bool mine = t[0] & bit, occ = t[3] & bit, legal = t[6] & bit;
+                o0.x = (mine ? 0x3F80u : 0u) | ((occ && !mine) ? 0x3F800000u : 0u);      // bf16 1.0 = 0x3F80
+                o0.y = (legal ? 0x3F80u : 0u) | 0x3F800000u;
+            } else {
+                float v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = c < P.in_planes ? P.obs[((size_t)(pos0 + g) * P.in_planes + c) * 81 + a] : 0.f;
+                o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+                o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+                o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+            }
+            const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * (uint32_t)SW;
+            *reinterpret_cast<uint4 *>(Y + swz(off)) = o0;
+            *reinterpret_cast<uint4 *>(Y + swz(off + 16)) = o1;
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (marks && pass < 4) marks[3 + 2 * pass] = clock64();
+        if (marks2 && pass == 0 && lane == 0 && warp < 8) marks2[100 + warp] = clock64();
+
+        // Layers are not separated by a block-wide barrier: input tile i of layer l+1 needs the activations of output
+        // tile i of layer l and the accumulator blocks of output tiles i-1, i, i+1 drained, nothing else.  Every role
+        // walks the layers of the pass on its own (lc = layers executed so far by this CTA: mbarrier phases); the issuer's
+        // whole walk sits inside ONE elected region - re-electing and re-converging the warp per layer cost ~600 cycles
+        // per layer.  Layer 0: planes(Y) -> X;  odd l (first conv of a block): X -> Y;  even l > 0: Y -> X, + residual X.
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int l = 0; l < n_layers; ++l) {
+                    const uint32_t lc = lcount + (uint32_t)l;
+                    if (l == n_layers - 1 && pass == n_pass - 1) griddep_launch(P.pdl_trigger == 2);
+                    const bool more_layers = l + 1 < n_layers;
+                    const bool more_passes = pass + 1 < n_pass;
+                    if (more_layers || more_passes) {
+                        // stream the NEXT layer's weights into the other buffer once the layer before this one (its
+                        // previous user) has been consumed by the tensor pipe
+                        const uint32_t nb = (lc & 1u) ^ 1u;
+                        uint8_t *Wn = W + nb * W_BUF;
+                        if (lc >= 1) mbar_wait(wfree + nb, ((lc - 1) >> 1) & 1u);
+                        if (marks2 && pass == 0) marks2[21 + 6 * l] = clock64();
+                        if (more_layers) {
+                            mbar_expect_tx(wfull + nb, 3u * W_DY + C * 32u);
+                            for (int dy = 0; dy < 3; ++dy) tma_load_2d(Wn + dy * W_DY, &tmW_conv, wfull + nb, 0, (l * 3 + dy) * N3);
+                            tma_load_2d(Wn + 3 * W_DY, &tmBias, wfull + nb, 0, (l + 1) * C);
+                        } else {
+                            mbar_expect_tx(wfull + nb, 3u * WS_DY + C * 32u);
+                            for (int dy = 0; dy < 3; ++dy) tma_load_2d(Wn + dy * W_DY, &tmW_stem, wfull + nb, 0, dy * N3);
+                            tma_load_2d(Wn + 3 * W_DY, &tmBias, wfull + nb, 0, 0);
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                const uint32_t base4 = smem_u32(smem) >> 4;
+                for (int l = 0; l < n_layers; ++l) {
+                    const uint32_t lc = lcount + (uint32_t)l;
+                    const uint32_t wb = lc & 1u;
+                    if (marks2 && pass == 0) marks2[20 + 6 * l] = clock64();
+                    mbar_wait(wfull + wb, (lc >> 1) & 1u);
+                    tc_fence_after();
+                    if (marks2 && pass == 0) marks2[16 + 6 * l] = clock64();
+                    uint64_t *prev = aready + ((lc - 1) & 1u) * BAR_STRIDE;
+                    const uint32_t pph = ((lc - 1) >> 1) & 1u;
+                    if (l == 0) {
+                        if (wb) issue_layer<0, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, P.dbg);
+                        else issue_layer<0, 0>(base4, tmem_base, tdone, prev, pph, wfree, P.dbg);
+                    } else if (l & 1) {
+                        if (wb) issue_layer<1, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, P.dbg);
+                        else issue_layer<1, 0>(base4, tmem_base, tdone, prev, pph, wfree, P.dbg);
+                    } else {
+                        if (wb) issue_layer<2, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, P.dbg);
+                        else issue_layer<2, 0>(base4, tmem_base, tdone, prev, pph, wfree, P.dbg);
+                    }
+                    if (marks2 && pass == 0) marks2[17 + 6 * l] = clock64();
+                }
+            }
+        } else if (warp >= FIRST_EPI) {
+            // ===== epilogue: ReLU + bf16 pack + store; two warps per TMEM lane quarter, tiles alternate =====
+            const int quarter = warp & 3, egroup = (warp - FIRST_EPI) >> 2;
+            const int i = 32 * quarter + lane;                       // lane of every tile = (position, board row)
+            const int g = i / PITCH, r = i - PITCH * g;
+            const bool valid = g < G && r < 9;
+            for (int l = 0; l < n_layers; ++l) {
+                const uint32_t lc = lcount + (uint32_t)l;
+                uint8_t *dst = (l & 1) ? Y : X;
+                for (int j = egroup; j < TILES; j += EPI_WARPS / 4) {
+                    mbar_wait(tdone + j, lc & 1u);
+                    tc_fence_after();
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(C * (j + 1)), acc);
+                    tmem_ld_wait();
+                    if (valid) {
+                        const uint32_t row_off = (uint32_t)(LEAD + 128 * j + i) * (uint32_t)SW;
+#pragma unroll
+                        for (int c = 0; c < C; c += 8) {
+                            uint4 ov;
+                            ov.x = relu_pack(acc[c], acc[c + 1], zero2);
+                            ov.y = relu_pack(acc[c + 2], acc[c + 3], zero2);
+                            ov.z = relu_pack(acc[c + 4], acc[c + 5], zero2);
+                            ov.w = relu_pack(acc[c + 6], acc[c + 7], zero2);
+                            *reinterpret_cast<uint4 *>(dst + swz(row_off + (uint32_t)c * 2u)) = ov;
+                        }
+                    }
+                    // rows written through the generic proxy are read by the next layer's UMMAs (async proxy); the
+                    // accumulator block is free again as well
+                    tc_fence_before();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(aready + (lc & 1u) * BAR_STRIDE + j);
+                    if (marks2 && pass == 0 && warp == FIRST_EPI && lane == 0) marks2[(j == 0 ? 18 : 19) + 6 * l] = clock64();
+                }
+            }
+        }
+        lcount += (uint32_t)n_layers;
+        // pass boundary: the next pass's planes overwrite Y and its stem overwrites the accumulators
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // The last layer left its activations in X like every other layer; they go out as whole 64-byte cells in cell
+        // order, i.e. 5184 contiguous bytes per position (written from the epilogue, lane = board row, every 16-byte
+        // store touched 32 different lines and the last layer's epilogue took 4 k cycles instead of 1 k).  The next
+        // pass's planes only touch Y, and its first epilogue comes after the barrier that follows them.
+        for (int idx = threadIdx.x; idx < G * 81 * 4; idx += THREADS) {
+            const int g = idx / 324, rem = idx - 324 * g;
+            const int a = rem >> 2, ch = rem & 3;
+            const int r = a / 9, cc = a - 9 * r;
+            const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * (uint32_t)SW + (uint32_t)ch * 16u;
+            reinterpret_cast<uint4 *>(P.out + ((size_t)(pos0 + g) * 81 + a) * C)[ch] = *reinterpret_cast<const uint4 *>(X + swz(off));
+        }
+        if (marks && pass < 4) marks[4 + 2 * pass] = clock64();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (marks) { marks[11] = clock64(); marks[12] = n_pass; marks[13] = p_end - p_begin; }
+}
+
+static size_t smem_bytes() { return 1024 + 2 * (size_t)BUF_BYTES + 2 * (size_t)W_BUF + C * SW + 4096 + (3 * BAR_STRIDE + 4) * 8 + 16 + GMAX * 12 * 4; }
+
+}  // namespace col
+
+bool trunk_col_supported(int C, int in_planes) { return C == col::C && in_planes <= 16; }
+
+// Weights of one layer as three [3C x K] blocks, one per kernel row ky: rows 0..C-1 hold kx = 2 (dx = +1, accumulates
+// into output tile i-1), rows C..2C-1 kx = 1, rows 2C..3C-1 kx = 0.  `w` is [co][ci][3][3] (PyTorch), K = ci padded to
+// k_pad columns.
+void trunk_col_pack(const float *w, int c_out, int c_in, int k_pad, __nv_bfloat16 *dst)
+{
+    for (int ky = 0; ky < 3; ++ky)
+        for (int b = 0; b < 3; ++b)
+            for (int co = 0; co < c_out; ++co)
+                for (int ci = 0; ci < k_pad; ++ci)
+                    dst[(((size_t)ky * 3 + b) * c_out + co) * k_pad + ci] =
+                        __float2bfloat16_rn(ci < c_in ? w[((size_t)co * c_in + ci) * 9 + ky * 3 + (2 - b)] : 0.f);
+}
+
+int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const CUtensorMap &bias_tiles, int n_conv,
+                     int in_planes, int batch, const int *count_dev, const uint32_t *states, const float *obs,
+                     __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st)
+{
+    col::Params P{};
+    P.count_dev = count_dev;
+    P.batch = batch;
+    P.n_conv = n_conv;
+    P.in_planes = in_planes;
+    P.states = states;
+    P.obs = obs;
+    P.out = out_flat;
+    P.pdl_trigger = pdl_trigger_enabled();
+    if (const char *dz = getenv("TACULT_COL_DBG")) P.dbg = atoi(dz);
+    static long long *timeline_dev = nullptr;
+    if (getenv("TACULT_FUSED_TIMELINE")) {
+        if (!timeline_dev) { cudaMalloc(&timeline_dev, 128 * sizeof(long long)); cudaMemset(timeline_dev, 0, 128 * sizeof(long long)); }
+        P.timeline = timeline_dev;
+    }
+    const size_t smem = col::smem_bytes();
+    const int grid = std::max(1, std::min(batch, sm_count));
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        TC_CUDA(cudaFuncSetAttribute(col::k_trunk_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev & 63] = true;
+    }
+    TC_CUDA(launch_chain(col::k_trunk_col, grid, col::THREADS, smem, st, w_stem, w_conv, bias_tiles, P));
+    if (P.timeline) {
+        long long m[128];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(m, timeline_dev, sizeof m, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[col marks] CTA 0, %lld positions in %lld passes; cycles since kernel entry: prologue done %lld | "
+                "dependency wait over %lld | pass 0 planes %lld done %lld | pass 1 planes %lld done %lld | exit %lld\n",
+                m[13], m[12], m[1] - m[0], m[2] - m[0], m[3] - m[0], m[4] - m[0], m[12] > 1 ? m[5] - m[0] : 0,
+                m[12] > 1 ? m[6] - m[0] : 0, m[11] - m[0]);
+        fprintf(stderr, "[col layers] pass 0, per layer: issuer at the weights barrier | issue start | issue end | epilogue of tile 0 | of tile 8 (cycles since kernel entry)\n");
+        for (int l = 0; l <= n_conv && l < 11; ++l)
+            fprintf(stderr, "[col layers] %2d: %7lld %7lld %7lld %7lld %7lld\n", l, m[20 + 6 * l] - m[0], m[16 + 6 * l] - m[0],
+                    m[17 + 6 * l] - m[0], m[18 + 6 * l] - m[0], m[19 + 6 * l] - m[0]);
+        fprintf(stderr, "[col layers] warps 0..7 after the planes barrier:");
+        for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld", m[100 + w] - m[0]);
+        fprintf(stderr, " | at the top of layer 0:");
+        for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld", m[108 + w] - m[0]);
+        fprintf(stderr, "\n[col layers] TMA of the next layer's weights issued at:");
+        for (int l = 0; l <= n_conv && l < 11; ++l) fprintf(stderr, " %lld", m[21 + 6 * l] - m[0]);
+        fprintf(stderr, "\n");
+    }
+    return TC_OK;
+}
+
+}  // namespace tc
