@@ -544,6 +544,7 @@ struct NetBF16Impl {
     // column-tiled fused trunk (C == 32): weights as [layer][ky][3C x K] blocks
     bool col = false;
     DevBuf<__nv_bfloat16> col_w_stem, col_w_conv;
+    DevBuf<float> col_bias;                // [1 + L][C]
     CUtensorMap map_col_stem, map_col_conv;
     DevBuf<__nv_bfloat16> conv_w_all;      // [n_conv][9][C][C]
     DevBuf<__nv_bfloat16> bias_tiles;      // [1 + n_conv][C][16]: bias as a K-major UMMA operand (hi, lo, 0...)
@@ -618,12 +619,20 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
         TC_TRY(upload(m.conv_b[l], f.conv_b[l]));
         TC_TRY(make_map(&m.map_conv_w[l], m.conv_w[l].p, (uint64_t)9 * C, C, (uint32_t)C, (uint32_t)m.block_k));
     }
-    // fc1: [E][c*81+p] (NCHW flatten, network.py:92) -> [E][p*C+c] to match the NHWC activations
+    // the column-tiled trunk (nn_trunk_col.cu) is the only producer of the fc1 input when it is on, and writes it with
+    // the cells of a position in column-major order
+    {
+        const char *fz = getenv("TACULT_FUSED"), *cz = getenv("TACULT_TRUNK_COL");
+        m.col = trunk_col_supported(C, I) && !share_sm && (!fz || atoi(fz) != 0) && (!cz || atoi(cz) != 0);
+    }
+    // fc1: [E][c*81+p] (NCHW flatten, network.py:92) -> [E][p'*C+c] to match the NHWC activations, p' = p or its transpose
     std::vector<__nv_bfloat16> fb((size_t)E * 81 * C);
     for (int e = 0; e < E; ++e)
         for (int c = 0; c < C; ++c)
-            for (int p = 0; p < 81; ++p)
-                fb[(size_t)e * 81 * C + (size_t)p * C + c] = __float2bfloat16_rn(f.fc1_w[(size_t)e * 81 * C + (size_t)c * 81 + p]);
+            for (int p = 0; p < 81; ++p) {
+                const int pp = m.col ? (p % 9) * 9 + p / 9 : p;
+                fb[(size_t)e * 81 * C + (size_t)pp * C + c] = __float2bfloat16_rn(f.fc1_w[(size_t)e * 81 * C + (size_t)c * 81 + p]);
+            }
     TC_TRY(upload(m.fc1_w, fb));
     TC_TRY(upload(m.fc1_b, f.fc1_b));
     std::vector<float> hw((size_t)E * 82), hb(f.pi_b);
@@ -706,6 +715,7 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
         const char *fz = getenv("TACULT_FUSED");
         int G = 0, T = 0;
         m.fused = m.stem_on_tensor && I <= 16 && (!fz || atoi(fz) != 0) && fused_plan(C, G, T);
+        TC_CHECK(m.fused || !m.col, TC_ESTATE, "column-tiled trunk selected but the fused path is unavailable (fc1 weights are already in its order)");
         if (m.fused) {
             // G, T are the largest group that fits.  Size the kernel for THIS instance's capacity instead: the group the
             // kernel would pick for a full batch (it re-balances from the live leaf count, never above these maxima), so
@@ -738,14 +748,13 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
             TC_TRY(upload(m.bias_tiles, btiles));
             TC_TRY(make_map(&m.map_bias_tiles, m.bias_tiles.p, (uint64_t)(1 + L) * C, 16, (uint32_t)C, 16));
             TC_TRY(make_map(&m.map_conv_w_all, m.conv_w_all.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)C, (uint32_t)C));
-            const char *cz = getenv("TACULT_TRUNK_COL");
-            m.col = trunk_col_supported(C, I) && !share_sm && (!cz || atoi(cz) != 0);
             if (m.col) {
                 std::vector<__nv_bfloat16> ws((size_t)9 * C * 16), wc(std::max<size_t>(1, L) * 9 * C * C, __float2bfloat16_rn(0.f));
                 trunk_col_pack(f.stem_w.data(), C, I, 16, ws.data());
                 for (size_t l = 0; l < L; ++l) trunk_col_pack(f.conv_w[l].data(), C, C, C, wc.data() + l * 9 * C * C);
                 TC_TRY(upload(m.col_w_stem, ws));
                 TC_TRY(upload(m.col_w_conv, wc));
+                TC_TRY(upload(m.col_bias, ball));
                 TC_TRY(make_map(&m.map_col_stem, m.col_w_stem.p, (uint64_t)9 * C, 16, (uint32_t)(3 * C), 16));
                 TC_TRY(make_map(&m.map_col_conv, m.col_w_conv.p, std::max<size_t>(1, L) * 9 * C, C, (uint32_t)(3 * C), (uint32_t)C));
             }
@@ -814,7 +823,7 @@ static int run_trunk(NetBF16Impl &m, int batch, const int *count_dev, const uint
     if (m.fused && to_flat && n_convs >= total) {
         prof->begin(TC_K_NN_CONV, st);
         if (m.col)
-            launch_trunk_col(m.map_col_stem, m.map_col_conv, m.map_bias_tiles, total, I, batch, count_dev, states, obs, m.flat.p,
+            launch_trunk_col(m.map_col_stem, m.map_col_conv, m.col_bias.p, total, I, batch, count_dev, states, obs, m.flat.p,
                              m.sm_count, st);
         else
             launch_trunk_fused(C, m.map_stem_w, m.map_conv_w_all, m.map_bias_tiles, m.fused_G, m.fused_T, total, I, batch,

@@ -20,7 +20,7 @@ int launch_trunk_fused(int C, const CUtensorMap &w_stem, const CUtensorMap &w_co
 // column-tiled variant for the 32-channel net (nn_trunk_col.cu): half the shared-memory operand traffic per layer
 bool trunk_col_supported(int C, int in_planes);
 void trunk_col_pack(const float *w, int c_out, int c_in, int k_pad, __nv_bfloat16 *dst);
-int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const CUtensorMap &bias_tiles, int n_conv,
+int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const float *bias_all, int n_conv,
                      int in_planes, int batch, const int *count_dev, const uint32_t *states, const float *obs,
                      __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st);
 

@@ -20,8 +20,12 @@
 // back to back (56 cycles per N = 96 UMMA, measured: tools/probes/umma_issue_probe.cu) and the summation order is
 // the same in every run, whereas two threads accumulating into overlapping columns serialise at ~250 cycles.  The
 // issue loop is straight-line code per tile: a rolled loop re-uses the uniform registers that carry the descriptors and
-// drops to 69 cycles per UMMA (same probe).  Bias = ones x bias tile (N = 32, overwrite) into each output block before
-// its first conv UMMA; residual = identity-tile UMMAs into the centre block.
+// drops to 69 cycles per UMMA (same probe).
+//
+// Bias and residual stay OFF the tensor pipe (as ones x bias-tile and identity-tile UMMAs they cost 9 x 46 and 18 x 58
+// cycles per layer, a quarter of the kernel): the epilogue that drains an accumulator block stores the bias of the
+// block's NEXT use back into it with tcgen05.st (TMEM writes run at 256 B/clk), so every conv UMMA simply accumulates;
+// the residual is added by the epilogue from the shared-memory row it is about to overwrite.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -48,13 +52,13 @@ constexpr int TILES = 9;                 // board columns
 constexpr int PITCH = 10;                // lanes per position: 9 board rows + 1 zero row
 constexpr int GMAX = 128 / PITCH;        // 12 positions per pass
 constexpr int FIRST_EPI = 4;             // warp 0: TMA, warp 1: UMMA issue, warps 2-3: plane encoding only
-constexpr int EPI_WARPS = 8;             // two per TMEM lane quarter
-constexpr int THREADS = 32 * (FIRST_EPI + EPI_WARPS);
+constexpr int EPI_GROUPS = 3;            // epilogue groups of four warps (one per TMEM lane quarter); tiles j = group (mod 3)
+constexpr int THREADS = 32 * (FIRST_EPI + 4 * EPI_GROUPS);
 constexpr int LEAD = 16, TAIL = 16;      // zero rows around the nine tiles (1 KB each: tiles stay 1024-aligned)
 constexpr int BUF_BYTES = (LEAD + 128 * TILES + TAIL) * SW;
 constexpr int W_DY = N3 * SW;            // one kernel row of a conv layer: [3C x C] bf16, K-major, 64-byte swizzle
 constexpr int WS_DY = N3 * 32;           // one kernel row of the stem:     [3C x 16]
-constexpr int W_BUF = 3 * W_DY + 1024;   // + bias tile [C x 16]
+constexpr int W_BUF = 3 * W_DY;
 constexpr int BAR_STRIDE = 16;
 constexpr int TILE_UNROLL = TC_COL_TILE_UNROLL;   // tiles of a layer issued as straight-line code
 
@@ -65,10 +69,10 @@ struct Params {
     int in_planes;
     const uint32_t *states;  // packed positions, or
     const float *obs;        // dense planes [row][in_planes][81]
-    __nv_bfloat16 *out;      // compact [row][81][C] (fc1 input)
+    const float *bias;       // [1 + n_conv][C] float32: stem, then every conv (BatchNorm folded)
+    __nv_bfloat16 *out;      // compact [row][board column][board row][C] (fc1 input; NOT the [row][cell][C] of the other trunks)
     long long *timeline;     // optional clock64 marks of CTA 0
     int pdl_trigger;
-    int dbg;                 // TACULT_COL_DBG bits (timing experiments only; results are wrong): 1 no bias, 2 no residual
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t off)       // byte offset inside a 1024-aligned buffer -> swizzled
@@ -114,7 +118,7 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t saddr)
 // travels through a vector register costs an R2UR, and those were measured at ~35 cycles each in the issuing thread:
 // 7 per tile made a tile cost 620 cycles instead of the 340-480 of its UMMAs (tools/probes/umma_issue_probe.cu).
 constexpr uint32_t X_OFF = 0, Y_OFF = BUF_BYTES, W_OFF = 2 * BUF_BYTES;
-constexpr uint32_t ID_OFF = W_OFF + 2 * W_BUF, ONES_OFF = ID_OFF + C * SW, BARS_OFF = ONES_OFF + 4096;
+constexpr uint32_t BARS_OFF = W_OFF + 2 * W_BUF;
 
 // low word of a descriptor: (address >> 4); the base is 1024-aligned, so the shift distributes
 template <int SWB>
@@ -126,45 +130,43 @@ __device__ __forceinline__ uint64_t desc_at(uint32_t base4, uint32_t off)
 }
 
 // Every UMMA of one layer, issued by one thread in a fixed order.  KIND 0: stem (planes in Y -> X), 1: first conv of a
-// block (X -> Y), 2: second conv (Y -> X, + residual X).  WB: weight buffer.  Input tile i accumulates into the blocks
-// of output tiles i-1, i, i+1; output tile j is complete (tdone[j]) once input tile j+1 has been issued.
+// block (X -> Y), 2: second conv (Y -> X).  WB: weight buffer.  Input tile i accumulates into the blocks of output tiles
+// i-1, i, i+1 (which hold the layer's bias when it starts); output tile j is complete (tdone[j]) once input tile j+1 has
+// been issued.
 template <int KIND, int WB>
 __device__ __forceinline__ void issue_layer(uint32_t base4, uint32_t tmem_base, uint64_t *tdone, uint64_t *prev, uint32_t pph,
-                                            uint64_t *wfree_bar, int dbg)
+                                            uint64_t *wfree_bar, uint64_t *next_wfull, uint32_t next_wph)
 {
     constexpr uint32_t SRC = KIND == 1 ? X_OFF : Y_OFF;
     constexpr uint32_t WL = W_OFF + WB * W_BUF;
-    const uint32_t idesc96 = make_instr_desc(N3), idesc32 = make_instr_desc(C);
-    const uint64_t ones_desc = desc_at<32>(base4, ONES_OFF), bias_desc = desc_at<32>(base4, WL + 3 * W_DY);
+    constexpr uint32_t BROW = KIND == 0 ? 32u : (uint32_t)SW;       // bytes per row of the weight tile
+    const uint32_t idesc96 = make_instr_desc(N3), idesc64 = make_instr_desc(2 * C);
 #pragma unroll(TILE_UNROLL)
     for (int i = 0; i < TILES; ++i) {
         if (KIND != 0) {
+            // the previous layer's output tile i is the A operand; its blocks i (waited for by tile i-1) and i+1 must
+            // have been drained and re-initialised
             if (i == 0) mbar_wait(prev, pph);
             if (i + 1 < TILES) mbar_wait(prev + i + 1, pph);
             tc_fence_after();
         }
-        const uint32_t d = tmem_base + (uint32_t)(C * i);
-        if (!(dbg & 1)) {
-            if (i == 0) umma_bf16(d + C, ones_desc, bias_desc, idesc32, 0u);
-            if (i + 1 < TILES) umma_bf16(d + 2 * C, ones_desc, bias_desc, idesc32, 0u);
-        }
-        constexpr uint32_t TILE0 = (uint32_t)(LEAD * SW);
-        const uint32_t tile = TILE0 + (uint32_t)(128 * SW * i);
+        // the next layer's weights landed long ago: take their wait off the layer boundary
+        if (i == TILES - 2 && next_wfull) mbar_wait(next_wfull, next_wph);
+        const uint32_t tile = (uint32_t)(LEAD * SW) + (uint32_t)(128 * SW * i);
+        // edge tiles: the outer block would go to a column that does not exist (N = 64, two blocks)
+        const uint32_t d = tmem_base + (uint32_t)(C * i) + (i == 0 ? (uint32_t)C : 0u);
+        const uint32_t wskip = i == 0 ? (uint32_t)C * BROW : 0u;
+        const uint32_t idesc = (i == 0 || i == TILES - 1) ? idesc64 : idesc96;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const uint32_t a = SRC + tile + (uint32_t)(dy * SW) - (uint32_t)SW;
             if (KIND == 0) {
-                umma_bf16(d, desc_at<SW>(base4, a), desc_at<32>(base4, WL + (uint32_t)(dy * W_DY)), idesc96, 1u);
+                umma_bf16(d, desc_at<SW>(base4, a), desc_at<32>(base4, WL + (uint32_t)(dy * W_DY) + wskip), idesc, 1u);
             } else {
 #pragma unroll
                 for (int k = 0; k < C / 16; ++k)
-                    umma_bf16(d, desc_at<SW>(base4, a + 32u * k), desc_at<SW>(base4, WL + (uint32_t)(dy * W_DY) + 32u * k), idesc96, 1u);
+                    umma_bf16(d, desc_at<SW>(base4, a + 32u * k), desc_at<SW>(base4, WL + (uint32_t)(dy * W_DY) + wskip + 32u * k), idesc, 1u);
             }
-        }
-        if (KIND == 2 && !(dbg & 2)) {
-#pragma unroll
-            for (int k = 0; k < C / 16; ++k)
-                umma_bf16(d + C, desc_at<SW>(base4, X_OFF + tile + 32u * k), desc_at<SW>(base4, ID_OFF + 32u * k), idesc32, 1u);
         }
         if (i >= 1) umma_commit(tdone + i - 1);
     }
@@ -173,21 +175,17 @@ __device__ __forceinline__ void issue_layer(uint32_t base4, uint32_t tmem_base, 
 }
 
 __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant__ CUtensorMap tmW_stem,
-                                                          const __grid_constant__ CUtensorMap tmW_conv,
-                                                          const __grid_constant__ CUtensorMap tmBias, Params P)
+                                                          const __grid_constant__ CUtensorMap tmW_conv, Params P)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *X = smem + X_OFF, *Y = smem + Y_OFF;
     uint8_t *W = smem + W_OFF;                                  // two layers' weights: layer n lives in buffer n & 1
-    uint8_t *Id = smem + ID_OFF;                                // identity [C x C]
-    uint8_t *Ones = smem + ONES_OFF;                            // 128 rows x 16 ones
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + BARS_OFF);
     uint64_t *tdone = bars;                                     // [j]: every UMMA into output tile j has completed
     uint64_t *aready = bars + BAR_STRIDE;                       // [layer & 1][j]: output tile j drained and written
     uint64_t *wfull = bars + 3 * BAR_STRIDE, *wfree = wfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfree + 2);
-    uint32_t *ptab = tmem_slot + 4;                             // [GMAX][12]: stones of the mover, all stones, legal cells
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_layers = 1 + P.n_conv;
@@ -200,14 +198,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmW_stem);
         tma_prefetch_desc(&tmW_conv);
-        tma_prefetch_desc(&tmBias);
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
-    // pad rows and spare lanes of both activation buffers must read as zero for ever: clear everything once
-    for (int i = threadIdx.x; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < C * SW / 16; i += THREADS) reinterpret_cast<uint4 *>(Id)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < 4096 / 16; i += THREADS)
-        reinterpret_cast<uint4 *>(Ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    if (threadIdx.x == 32) {
+        for (int j = 0; j < TILES; ++j) mbar_init(tdone + j, 1);
+        for (int b = 0; b < 2; ++b)
+            for (int j = 0; j < TILES; ++j) mbar_init(aready + b * BAR_STRIDE + j, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, 1); }
+        fence_barrier_init();
+    }
+    // The rows a shifted descriptor can reach from a live row without meaning to must read as zero for ever: the lead and
+    // tail rows, the pad row after every position (lanes 9, 19, ...) and the spare lanes 120..127 of every tile.  Nothing
+    // ever writes them.  Rows of positions a pass does not use keep whatever they held: a GEMM row only sees its own
+    // position, and those rows are neither stored nor copied out.
+    for (int i = threadIdx.x; i < 2 * (LEAD + TAIL) * 4; i += THREADS) {
+        const int buf = i / ((LEAD + TAIL) * 4), rem = i - buf * (LEAD + TAIL) * 4;
+        const int row = rem >> 2, ch = rem & 3;
+        const int abs_row = row < LEAD ? row : LEAD + 128 * TILES + (row - LEAD);
+        *reinterpret_cast<uint4 *>(smem + buf * BUF_BYTES + abs_row * SW + ch * 16) = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = threadIdx.x; i < 2 * TILES * 20 * 4; i += THREADS) {
+        const int ch = i & 3, k = (i >> 2) % 20, t = (i >> 2) / 20;               // t = buffer * TILES + tile
+        const int buf = t / TILES, tile = t - buf * TILES;
+        const int lane_row = k < GMAX ? PITCH * k + 9 : 120 + (k - GMAX);
+        *reinterpret_cast<uint4 *>(smem + buf * BUF_BYTES + (LEAD + 128 * tile + lane_row) * SW + ch * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
+    // the stem's weights, and its bias as the initial value of the accumulator blocks (later passes and layers find the
+    // bias the epilogue left there)
+    if (warp == 0 && lane == 0) {
+        mbar_expect_tx(wfull, 3u * WS_DY);
+        for (int dy = 0; dy < 3; ++dy) tma_load_2d(W + dy * W_DY, &tmW_stem, wfull, 0, dy * N3);
+    }
+    if (warp >= FIRST_EPI && warp < FIRST_EPI + 4) {
+        uint32_t b0[32];
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(P.bias + c));
+            b0[c] = __float_as_uint(v.x); b0[c + 1] = __float_as_uint(v.y); b0[c + 2] = __float_as_uint(v.z); b0[c + 3] = __float_as_uint(v.w);
+        }
+        for (int j = 0; j < TILES; ++j) tmem_st32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(C * (j + 1)), b0);
+        tmem_st_wait();
+        tc_fence_before();
+    }
 
     // ---- from here on the leaf count and the leaf positions written by the descent kernel are read ----
     if (marks) marks[1] = clock64();
@@ -218,29 +255,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
     const int p_begin = min(count, (int)blockIdx.x * per), p_end = min(count, p_begin + per);
     const int n_pass = (p_end - p_begin + GMAX - 1) / GMAX;
-    if (n_pass == 0 && threadIdx.x == 0) griddep_launch(P.pdl_trigger == 2);
-    if (threadIdx.x == 0) {
-        for (int j = 0; j < TILES; ++j) mbar_init(tdone + j, 1);
-        for (int b = 0; b < 2; ++b)
-            for (int j = 0; j < TILES; ++j) mbar_init(aready + b * BAR_STRIDE + j, 4);
-        for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, 1); }
-        fence_barrier_init();
+    if (n_pass == 0 && threadIdx.x == 0) {
+        griddep_launch(P.pdl_trigger == 2);
+        mbar_wait(wfull, 0u);                   // nothing to do: let the stem weights land before the CTA retires
     }
-    __syncthreads();
-    if (threadIdx.x < C)            // identity, K-major rows of SW bytes in the swizzle pattern
-        *reinterpret_cast<__nv_bfloat16 *>(Id + swz((uint32_t)threadIdx.x * SW + (uint32_t)threadIdx.x * 2u)) = __float2bfloat16_rn(1.f);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
-
     uint32_t lcount = 0;       // layers executed so far by this CTA (mbarrier phase = lcount & 1)
-    if (warp == 0 && lane == 0 && n_pass > 0) {
-        mbar_expect_tx(wfull, 3u * WS_DY + C * 32u);
-        for (int dy = 0; dy < 3; ++dy) tma_load_2d(W + dy * W_DY, &tmW_stem, wfull, 0, dy * N3);
-        tma_load_2d(W + 3 * W_DY, &tmBias, wfull, 0, 0);
-    }
+    // packed position of (pass, warp): lane k < 8 holds word k
+    uint32_t state_word = 0u;
+    if (P.states && p_begin + warp < p_end && lane < 8) state_word = P.states[8 * (size_t)(p_begin + warp) + lane];
 
     const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
@@ -248,52 +270,54 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     for (int pass = 0; pass < n_pass; ++pass) {
         const int pos0 = p_begin + pass * GMAX;
         const int G = min(GMAX, p_end - pos0);
-        // ---- observation planes of the pass -> channels 0..15 of the rows in Y (pad rows are never touched).  The legal
-        //      mask of a position is computed ONCE, by a warp (rules_warp.cuh), not once per cell: per-cell scalar
-        //      rules made this phase 8.7 k cycles per pass, a fifth of the kernel ----
+        // ---- observation planes of the pass -> channels 0..15 of the rows in Y (pad rows are never touched).  One warp
+        //      per position: the legal mask is computed ONCE, by the warp (rules_warp.cuh), and each lane then writes its
+        //      cells lane, lane + 32, lane + 64 (per-cell scalar rules made this phase 8.7 k cycles per pass, a fifth of
+        //      the kernel).  The position's words were fetched while the previous pass was still running ----
         if (P.states) {
-            for (int g = warp; g < G; g += THREADS / 32) {
-                const uint32_t w = lane < 8 ? P.states[8 * (size_t)(pos0 + g) + lane] : 0u;
+            if (warp < G) {
                 uint32_t wd[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) wd[k] = __shfl_sync(0xFFFFFFFFu, w, k);
+                for (int k = 0; k < 8; ++k) wd[k] = __shfl_sync(0xFFFFFFFFu, state_word, k);
                 const Pos p = unpack(wd);
                 uint32_t am[3], mm[3], oo[3];
                 int status;
                 warp_legal_mask<true>(p, lane, am, status, mm, oo);
-                if (lane < 3) {
-                    ptab[g * 12 + lane] = mm[lane];
-                    ptab[g * 12 + 3 + lane] = oo[lane];
-                    ptab[g * 12 + 6 + lane] = am[lane];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int a = lane + 32 * q;
+                    if (a < 81) {
+                        const bool mine = (mm[q] >> lane) & 1u, occ = (oo[q] >> lane) & 1u, legal = (am[q] >> lane) & 1u;
+                        const int r = (a * 57) >> 9, cc = a - 9 * r;
+                        const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * warp + r) * (uint32_t)SW;
+                        // bf16 1.0 = 0x3F80: planes mine, theirs | legal, ones; channels 4..15 are zero
+                        *reinterpret_cast<uint4 *>(Y + swz(off)) =
+                            make_uint4((mine ? 0x3F80u : 0u) | ((occ && !mine) ? 0x3F800000u : 0u), (legal ? 0x3F80u : 0u) | 0x3F800000u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(Y + swz(off + 16)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
             }
-            __syncthreads();
-        }
-        // consecutive threads write consecutive rows of one tile (64 bytes apart: conflict-free 16-byte stores); cells of
-        // one board row live 8 KB apart and would all fall on the same banks
-        for (int idx = threadIdx.x; idx < G * 81; idx += THREADS) {
-            const int cc = idx / (9 * G), gr = idx - 9 * G * cc;
-            const int g = gr / 9, r = gr - 9 * g;
-            const int a = 9 * r + cc;
-            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = make_uint4(0u, 0u, 0u, 0u);
-            if (P.states) {
-                const uint32_t *t = ptab + g * 12 + (a >> 5);
-                const uint32_t bit = 1u << (a & 31);
-                const bool mine = t[0] & bit, occ = t[3] & bit, legal = t[6] & bit;
-                o0.x = (mine ? 0x3F80u : 0u) | ((occ && !mine) ? 0x3F800000u : 0u);      // bf16 1.0 = 0x3F80
-                o0.y = (legal ? 0x3F80u : 0u) | 0x3F800000u;
-            } else {
+            // next pass: start the fetch now, use it after this pass's layers
+            if (pos0 + GMAX + warp < p_end && lane < 8) state_word = P.states[8 * (size_t)(pos0 + GMAX + warp) + lane];
+        } else {
+            // dense planes: consecutive threads write consecutive rows of one tile (64 bytes apart: conflict-free 16-byte
+            // stores); cells of one board row live 8 KB apart and would all fall on the same banks
+            for (int idx = threadIdx.x; idx < G * 81; idx += THREADS) {
+                const int cc = idx / (9 * G), gr = idx - 9 * G * cc;
+                const int g = gr / 9, r = gr - 9 * g;
+                const int a = 9 * r + cc;
                 float v[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) v[c] = c < P.in_planes ? P.obs[((size_t)(pos0 + g) * P.in_planes + c) * 81 + a] : 0.f;
+                uint4 o0, o1;
                 o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
                 o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
                 o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
                 o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * (uint32_t)SW;
+                *reinterpret_cast<uint4 *>(Y + swz(off)) = o0;
+                *reinterpret_cast<uint4 *>(Y + swz(off + 16)) = o1;
             }
-            const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * (uint32_t)SW;
-            *reinterpret_cast<uint4 *>(Y + swz(off)) = o0;
-            *reinterpret_cast<uint4 *>(Y + swz(off + 16)) = o1;
         }
         fence_async_smem();
         __syncthreads();
@@ -320,13 +344,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
                         if (lc >= 1) mbar_wait(wfree + nb, ((lc - 1) >> 1) & 1u);
                         if (marks2 && pass == 0) marks2[21 + 6 * l] = clock64();
                         if (more_layers) {
-                            mbar_expect_tx(wfull + nb, 3u * W_DY + C * 32u);
+                            mbar_expect_tx(wfull + nb, 3u * W_DY);
                             for (int dy = 0; dy < 3; ++dy) tma_load_2d(Wn + dy * W_DY, &tmW_conv, wfull + nb, 0, (l * 3 + dy) * N3);
-                            tma_load_2d(Wn + 3 * W_DY, &tmBias, wfull + nb, 0, (l + 1) * C);
                         } else {
-                            mbar_expect_tx(wfull + nb, 3u * WS_DY + C * 32u);
+                            mbar_expect_tx(wfull + nb, 3u * WS_DY);
                             for (int dy = 0; dy < 3; ++dy) tma_load_2d(Wn + dy * W_DY, &tmW_stem, wfull + nb, 0, dy * N3);
-                            tma_load_2d(Wn + 3 * W_DY, &tmBias, wfull + nb, 0, 0);
                         }
                     }
                 }
@@ -338,26 +360,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
                     const uint32_t lc = lcount + (uint32_t)l;
                     const uint32_t wb = lc & 1u;
                     if (marks2 && pass == 0) marks2[20 + 6 * l] = clock64();
-                    mbar_wait(wfull + wb, (lc >> 1) & 1u);
+                    if (l == 0) mbar_wait(wfull + wb, (lc >> 1) & 1u);        // later layers: waited for inside the layer before
                     tc_fence_after();
                     if (marks2 && pass == 0) marks2[16 + 6 * l] = clock64();
                     uint64_t *prev = aready + ((lc - 1) & 1u) * BAR_STRIDE;
                     const uint32_t pph = ((lc - 1) >> 1) & 1u;
+                    uint64_t *nwf = l + 1 < n_layers ? wfull + (wb ^ 1u) : nullptr;
+                    const uint32_t nwph = ((lc + 1) >> 1) & 1u;
                     if (l == 0) {
-                        if (wb) issue_layer<0, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, P.dbg);
-                        else issue_layer<0, 0>(base4, tmem_base, tdone, prev, pph, wfree, P.dbg);
+                        if (wb) issue_layer<0, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph);
+                        else issue_layer<0, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph);
                     } else if (l & 1) {
-                        if (wb) issue_layer<1, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, P.dbg);
-                        else issue_layer<1, 0>(base4, tmem_base, tdone, prev, pph, wfree, P.dbg);
+                        if (wb) issue_layer<1, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph);
+                        else issue_layer<1, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph);
                     } else {
-                        if (wb) issue_layer<2, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, P.dbg);
-                        else issue_layer<2, 0>(base4, tmem_base, tdone, prev, pph, wfree, P.dbg);
+                        if (wb) issue_layer<2, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph);
+                        else issue_layer<2, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph);
                     }
                     if (marks2 && pass == 0) marks2[17 + 6 * l] = clock64();
                 }
             }
         } else if (warp >= FIRST_EPI) {
-            // ===== epilogue: ReLU + bf16 pack + store; two warps per TMEM lane quarter, tiles alternate =====
+            // ===== epilogue: (+ residual) ReLU, bf16 pack, store; the drained block gets the bias of its next use =====
             const int quarter = warp & 3, egroup = (warp - FIRST_EPI) >> 2;
             const int i = 32 * quarter + lane;                       // lane of every tile = (position, board row)
             const int g = i / PITCH, r = i - PITCH * g;
@@ -365,26 +389,55 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
             for (int l = 0; l < n_layers; ++l) {
                 const uint32_t lc = lcount + (uint32_t)l;
                 uint8_t *dst = (l & 1) ? Y : X;
-                for (int j = egroup; j < TILES; j += EPI_WARPS / 4) {
+                const bool residual = l > 0 && !(l & 1);             // second conv of a block: + the block's input, in X
+                const bool last = l == n_layers - 1;
+                uint32_t nb[32];                                     // bias of the next layer (the next pass's stem after the last)
+                {
+                    const float *bsrc = P.bias + (l + 1 < n_layers ? (l + 1) * C : 0);
+#pragma unroll
+                    for (int c = 0; c < C; c += 4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(bsrc + c));
+                        nb[c] = __float_as_uint(v.x); nb[c + 1] = __float_as_uint(v.y);
+                        nb[c + 2] = __float_as_uint(v.z); nb[c + 3] = __float_as_uint(v.w);
+                    }
+                }
+                for (int j = egroup; j < TILES; j += EPI_GROUPS) {
+                    const uint32_t t_addr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(C * (j + 1));
                     mbar_wait(tdone + j, lc & 1u);
                     tc_fence_after();
                     uint32_t acc[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(C * (j + 1)), acc);
+                    tmem_ld32(t_addr, acc);
                     tmem_ld_wait();
+                    tmem_st32(t_addr, nb);
                     if (valid) {
                         const uint32_t row_off = (uint32_t)(LEAD + 128 * j + i) * (uint32_t)SW;
 #pragma unroll
                         for (int c = 0; c < C; c += 8) {
+                            uint4 *cell = reinterpret_cast<uint4 *>(dst + swz(row_off + (uint32_t)c * 2u));
+                            if (residual) {
+                                const uint4 x = *reinterpret_cast<const uint4 *>(X + swz(row_off + (uint32_t)c * 2u));
+                                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    acc[c + 2 * q] = __float_as_uint(__uint_as_float(acc[c + 2 * q]) + __uint_as_float(xs[q] << 16));
+                                    acc[c + 2 * q + 1] = __float_as_uint(__uint_as_float(acc[c + 2 * q + 1]) + __uint_as_float(xs[q] & 0xFFFF0000u));
+                                }
+                            }
                             uint4 ov;
                             ov.x = relu_pack(acc[c], acc[c + 1], zero2);
                             ov.y = relu_pack(acc[c + 2], acc[c + 3], zero2);
                             ov.z = relu_pack(acc[c + 4], acc[c + 5], zero2);
                             ov.w = relu_pack(acc[c + 6], acc[c + 7], zero2);
-                            *reinterpret_cast<uint4 *>(dst + swz(row_off + (uint32_t)c * 2u)) = ov;
+                            // the fc1 input is column-major per position ([row][board column][board row][C], the K
+                            // order fc1's weights are uploaded in for this kernel): the nine rows of a position's column
+                            // are 576 contiguous bytes, written by nine adjacent lanes
+                            if (last) *reinterpret_cast<uint4 *>(P.out + ((size_t)(pos0 + g) * 81 + 9 * j + r) * C + c) = ov;
+                            else *cell = ov;
                         }
                     }
                     // rows written through the generic proxy are read by the next layer's UMMAs (async proxy); the
-                    // accumulator block is free again as well
+                    // accumulator block holds its next bias
+                    tmem_st_wait();
                     tc_fence_before();
                     fence_async_smem();
                     __syncwarp();
@@ -398,17 +451,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        // The last layer left its activations in X like every other layer; they go out as whole 64-byte cells in cell
-        // order, i.e. 5184 contiguous bytes per position (written from the epilogue, lane = board row, every 16-byte
-        // store touched 32 different lines and the last layer's epilogue took 4 k cycles instead of 1 k).  The next
-        // pass's planes only touch Y, and its first epilogue comes after the barrier that follows them.
-        for (int idx = threadIdx.x; idx < G * 81 * 4; idx += THREADS) {
-            const int g = idx / 324, rem = idx - 324 * g;
-            const int a = rem >> 2, ch = rem & 3;
-            const int r = a / 9, cc = a - 9 * r;
-            const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * (uint32_t)SW + (uint32_t)ch * 16u;
-            reinterpret_cast<uint4 *>(P.out + ((size_t)(pos0 + g) * 81 + a) * C)[ch] = *reinterpret_cast<const uint4 *>(X + swz(off));
-        }
         if (marks && pass < 4) marks[4 + 2 * pass] = clock64();
     }
     tc_fence_before();
@@ -417,7 +459,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     if (marks) { marks[11] = clock64(); marks[12] = n_pass; marks[13] = p_end - p_begin; }
 }
 
-static size_t smem_bytes() { return 1024 + 2 * (size_t)BUF_BYTES + 2 * (size_t)W_BUF + C * SW + 4096 + (3 * BAR_STRIDE + 4) * 8 + 16 + GMAX * 12 * 4; }
+static size_t smem_bytes() { return 1024 + 2 * (size_t)BUF_BYTES + 2 * (size_t)W_BUF + (3 * BAR_STRIDE + 4) * 8 + 16; }
 
 }  // namespace col
 
@@ -436,7 +478,7 @@ void trunk_col_pack(const float *w, int c_out, int c_in, int k_pad, __nv_bfloat1
                         __float2bfloat16_rn(ci < c_in ? w[((size_t)co * c_in + ci) * 9 + ky * 3 + (2 - b)] : 0.f);
 }
 
-int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const CUtensorMap &bias_tiles, int n_conv,
+int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const float *bias_all, int n_conv,
                      int in_planes, int batch, const int *count_dev, const uint32_t *states, const float *obs,
                      __nv_bfloat16 *out_flat, int sm_count, cudaStream_t st)
 {
@@ -448,8 +490,8 @@ int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const
     P.states = states;
     P.obs = obs;
     P.out = out_flat;
+    P.bias = bias_all;
     P.pdl_trigger = pdl_trigger_enabled();
-    if (const char *dz = getenv("TACULT_COL_DBG")) P.dbg = atoi(dz);
     static long long *timeline_dev = nullptr;
     if (getenv("TACULT_FUSED_TIMELINE")) {
         if (!timeline_dev) { cudaMalloc(&timeline_dev, 128 * sizeof(long long)); cudaMemset(timeline_dev, 0, 128 * sizeof(long long)); }
@@ -464,7 +506,7 @@ int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const
         TC_CUDA(cudaFuncSetAttribute(col::k_trunk_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev & 63] = true;
     }
-    TC_CUDA(launch_chain(col::k_trunk_col, grid, col::THREADS, smem, st, w_stem, w_conv, bias_tiles, P));
+    TC_CUDA(launch_chain(col::k_trunk_col, grid, col::THREADS, smem, st, w_stem, w_conv, P));
     if (P.timeline) {
         long long m[128];
         cudaStreamSynchronize(st);
