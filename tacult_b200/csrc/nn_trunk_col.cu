@@ -12,20 +12,32 @@
 //     and accumulates into the 96 TMEM columns that hold output tiles i-1, i, i+1 side by side.  The sums over dx
 //     happen in the accumulators; no lane ever needs another lane's value, and the epilogue is the old one
 //     (one tcgen05.ld, ReLU, pack, store).
-// Per tile and layer: 6 UMMAs of N = 96 (56 cycles each) instead of 18 of N = 32 (40 each); 31 KB of operands per
-// position and layer instead of 78 KB.  Accumulators: 11 blocks of 32 columns (out tiles -1 and 9 are dummies that
-// catch the edge tiles' outer blocks).
+// Per tile and layer: 6 UMMAs of N = 96 (56 cycles each; N = 64 for the two edge columns, whose outer block has no
+// output column) instead of 18 of N = 32 (40 each); 31 KB of operands per position and layer instead of 78 KB.
+// Accumulators: 11 blocks of 32 TMEM columns (out tiles -1 and 9 are dummies).
 //
-// One thread issues every UMMA, in a fixed order: accumulating UMMAs of one thread into the same columns run
-// back to back (56 cycles per N = 96 UMMA, measured: tools/probes/umma_issue_probe.cu) and the summation order is
-// the same in every run, whereas two threads accumulating into overlapping columns serialise at ~250 cycles.  The
-// issue loop is straight-line code per tile: a rolled loop re-uses the uniform registers that carry the descriptors and
-// drops to 69 cycles per UMMA (same probe).
+// One thread issues every UMMA, in a fixed order: accumulating UMMAs of one thread into the same columns run back to
+// back (56 cycles per N = 96 UMMA, measured: tools/probes/umma_issue_probe.cu) and the summation order is the same in
+// every run, whereas two threads accumulating into overlapping columns serialise at ~250 cycles.  The issue code is
+// straight-line per layer kind and weight buffer, every descriptor a (shared-memory base + compile-time constant):
+// descriptors that travel through vector registers (R2UR) or a rolled tile loop cost 70-100 cycles per UMMA.  The whole
+// walk over passes and layers sits inside ONE elected region (re-electing per layer cost ~600 cycles per layer).
 //
 // Bias and residual stay OFF the tensor pipe (as ones x bias-tile and identity-tile UMMAs they cost 9 x 46 and 18 x 58
 // cycles per layer, a quarter of the kernel): the epilogue that drains an accumulator block stores the bias of the
 // block's NEXT use back into it with tcgen05.st (TMEM writes run at 256 B/clk), so every conv UMMA simply accumulates;
 // the residual is added by the epilogue from the shared-memory row it is about to overwrite.
+//
+// The passes of a CTA and their layers form one stream without a block-wide barrier: the stem of pass p+1 follows the
+// last layer of pass p like any layer follows another (per-tile mbarriers), its observation planes having been encoded
+// into a buffer of their own by two otherwise idle warps while pass p ran.  The planes come from ONE warp-cooperative
+// legal-mask evaluation per position (rules_warp.cuh); per-cell scalar rules took a fifth of the kernel.
+//
+// What bounds it: shared-memory bandwidth.  Per tile and layer the tensor pipe fetches 42 KB of operands and the
+// epilogue moves 8-16 KB (activation rows out, residual rows in) through the same 128 B/clk: 390-450 cycles, and the
+// measured layer period is 3.85 k cycles for 9 tiles.  Roles: warp 0 streams the next layer's weights (TMA, double
+// buffered), warp 1 issues, warps 2-3 encode planes, warps 4-15 are three epilogue groups of four (one warp per TMEM
+// lane quarter; group e owns tiles j = e mod 3).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -51,7 +63,7 @@ constexpr int N3 = 3 * C;
 constexpr int TILES = 9;                 // board columns
 constexpr int PITCH = 10;                // lanes per position: 9 board rows + 1 zero row
 constexpr int GMAX = 128 / PITCH;        // 12 positions per pass
-constexpr int FIRST_EPI = 4;             // warp 0: TMA, warp 1: UMMA issue, warps 2-3: plane encoding only
+constexpr int FIRST_EPI = 4;             // warp 0: TMA, warp 1: UMMA issue, warps 2-3: planes of the NEXT pass
 constexpr int EPI_GROUPS = 3;            // epilogue groups of four warps (one per TMEM lane quarter); tiles j = group (mod 3)
 constexpr int THREADS = 32 * (FIRST_EPI + 4 * EPI_GROUPS);
 constexpr int LEAD = 16, TAIL = 16;      // zero rows around the nine tiles (1 KB each: tiles stay 1024-aligned)
@@ -79,6 +91,7 @@ __device__ __forceinline__ uint32_t swz(uint32_t off)       // byte offset insid
 {
     return off ^ (((off >> 7) & (uint32_t)(SW / 16 - 1)) << 4);
 }
+__device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }      // rows of 32 bytes
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -118,7 +131,9 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t saddr)
 // travels through a vector register costs an R2UR, and those were measured at ~35 cycles each in the issuing thread:
 // 7 per tile made a tile cost 620 cycles instead of the 340-480 of its UMMAs (tools/probes/umma_issue_probe.cu).
 constexpr uint32_t X_OFF = 0, Y_OFF = BUF_BYTES, W_OFF = 2 * BUF_BYTES;
-constexpr uint32_t BARS_OFF = W_OFF + 2 * W_BUF;
+constexpr uint32_t P_OFF = W_OFF + 2 * W_BUF;                    // observation planes of one pass: rows of 32 bytes (K = 16)
+constexpr uint32_t PBUF_BYTES = (LEAD + 128 * TILES + TAIL) * 32;
+constexpr uint32_t BARS_OFF = P_OFF + PBUF_BYTES;
 
 // low word of a descriptor: (address >> 4); the base is 1024-aligned, so the shift distributes
 template <int SWB>
@@ -135,33 +150,36 @@ __device__ __forceinline__ uint64_t desc_at(uint32_t base4, uint32_t off)
 // been issued.
 template <int KIND, int WB>
 __device__ __forceinline__ void issue_layer(uint32_t base4, uint32_t tmem_base, uint64_t *tdone, uint64_t *prev, uint32_t pph,
-                                            uint64_t *wfree_bar, uint64_t *next_wfull, uint32_t next_wph)
+                                            uint64_t *wfree_bar, uint64_t *next_wfull, uint32_t next_wph, bool first_of_kernel,
+                                            uint64_t *pfree)
 {
-    constexpr uint32_t SRC = KIND == 1 ? X_OFF : Y_OFF;
+    constexpr uint32_t SRC = KIND == 0 ? P_OFF : (KIND == 1 ? X_OFF : Y_OFF);
+    constexpr uint32_t AROW = KIND == 0 ? 32u : (uint32_t)SW;       // bytes per row of the A operand
     constexpr uint32_t WL = W_OFF + WB * W_BUF;
     constexpr uint32_t BROW = KIND == 0 ? 32u : (uint32_t)SW;       // bytes per row of the weight tile
     const uint32_t idesc96 = make_instr_desc(N3), idesc64 = make_instr_desc(2 * C);
 #pragma unroll(TILE_UNROLL)
     for (int i = 0; i < TILES; ++i) {
-        if (KIND != 0) {
-            // the previous layer's output tile i is the A operand; its blocks i (waited for by tile i-1) and i+1 must
-            // have been drained and re-initialised
+        if (KIND != 0 || !first_of_kernel) {
+            // the previous layer's output tile i is the A operand (not for a stem: its planes were waited for by the
+            // caller); its blocks i (waited for by tile i-1) and i+1 must have been drained and re-initialised.  The stem
+            // of a later pass follows the last layer of the pass before it like any other layer.
             if (i == 0) mbar_wait(prev, pph);
             if (i + 1 < TILES) mbar_wait(prev + i + 1, pph);
             tc_fence_after();
         }
         // the next layer's weights landed long ago: take their wait off the layer boundary
         if (i == TILES - 2 && next_wfull) mbar_wait(next_wfull, next_wph);
-        const uint32_t tile = (uint32_t)(LEAD * SW) + (uint32_t)(128 * SW * i);
+        const uint32_t tile = (uint32_t)LEAD * AROW + 128u * AROW * (uint32_t)i;
         // edge tiles: the outer block would go to a column that does not exist (N = 64, two blocks)
         const uint32_t d = tmem_base + (uint32_t)(C * i) + (i == 0 ? (uint32_t)C : 0u);
         const uint32_t wskip = i == 0 ? (uint32_t)C * BROW : 0u;
         const uint32_t idesc = (i == 0 || i == TILES - 1) ? idesc64 : idesc96;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t a = SRC + tile + (uint32_t)(dy * SW) - (uint32_t)SW;
+            const uint32_t a = SRC + tile + (uint32_t)dy * AROW - AROW;
             if (KIND == 0) {
-                umma_bf16(d, desc_at<SW>(base4, a), desc_at<32>(base4, WL + (uint32_t)(dy * W_DY) + wskip), idesc, 1u);
+                umma_bf16(d, desc_at<32>(base4, a), desc_at<32>(base4, WL + (uint32_t)(dy * W_DY) + wskip), idesc, 1u);
             } else {
 #pragma unroll
                 for (int k = 0; k < C / 16; ++k)
@@ -172,6 +190,7 @@ __device__ __forceinline__ void issue_layer(uint32_t base4, uint32_t tmem_base, 
     }
     umma_commit(tdone + TILES - 1);
     umma_commit(wfree_bar);
+    if (KIND == 0) umma_commit(pfree);        // the planes buffer has been consumed: the next pass's planes may be written
 }
 
 __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant__ CUtensorMap tmW_stem,
@@ -185,7 +204,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     uint64_t *tdone = bars;                                     // [j]: every UMMA into output tile j has completed
     uint64_t *aready = bars + BAR_STRIDE;                       // [layer & 1][j]: output tile j drained and written
     uint64_t *wfull = bars + 3 * BAR_STRIDE, *wfree = wfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfree + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfree + 4);        // wfree + 2, + 3: `pready`, `pfree`
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_layers = 1 + P.n_conv;
@@ -205,6 +224,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         for (int b = 0; b < 2; ++b)
             for (int j = 0; j < TILES; ++j) mbar_init(aready + b * BAR_STRIDE + j, 4);
         for (int b = 0; b < 2; ++b) { mbar_init(wfull + b, 1); mbar_init(wfree + b, 1); }
+        mbar_init(wfree + 2, FIRST_EPI - 2);      // pready: one arrival per plane warp
+        mbar_init(wfree + 3, 1);                  // pfree
         fence_barrier_init();
     }
     // The rows a shifted descriptor can reach from a live row without meaning to must read as zero for ever: the lead and
@@ -217,6 +238,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         const int abs_row = row < LEAD ? row : LEAD + 128 * TILES + (row - LEAD);
         *reinterpret_cast<uint4 *>(smem + buf * BUF_BYTES + abs_row * SW + ch * 16) = make_uint4(0, 0, 0, 0);
     }
+    for (int i = threadIdx.x; i < (int)PBUF_BYTES / 16; i += THREADS)          // the planes buffer: cleared whole (38 KB)
+        reinterpret_cast<uint4 *>(smem + P_OFF)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < 2 * TILES * 20 * 4; i += THREADS) {
         const int ch = i & 3, k = (i >> 2) % 20, t = (i >> 2) / 20;               // t = buffer * TILES + tile
         const int buf = t / TILES, tile = t - buf * TILES;
@@ -259,80 +282,82 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         griddep_launch(P.pdl_trigger == 2);
         mbar_wait(wfull, 0u);                   // nothing to do: let the stem weights land before the CTA retires
     }
-    uint32_t lcount = 0;       // layers executed so far by this CTA (mbarrier phase = lcount & 1)
-    // packed position of (pass, warp): lane k < 8 holds word k
-    uint32_t state_word = 0u;
-    if (P.states && p_begin + warp < p_end && lane < 8) state_word = P.states[8 * (size_t)(p_begin + warp) + lane];
-
-    const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y);
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+    uint8_t *Pl = smem + P_OFF;
+    uint64_t *pready = wfree + 2;      // planes of pass p >= 1 are in the planes buffer (completes once per such pass)
+    uint64_t *pfree = wfree + 3;       // the stem of a pass has been consumed by the tensor pipe (completes once per pass)
 
-    for (int pass = 0; pass < n_pass; ++pass) {
-        const int pos0 = p_begin + pass * GMAX;
-        const int G = min(GMAX, p_end - pos0);
-        // ---- observation planes of the pass -> channels 0..15 of the rows in Y (pad rows are never touched).  One warp
-        //      per position: the legal mask is computed ONCE, by the warp (rules_warp.cuh), and each lane then writes its
-        //      cells lane, lane + 32, lane + 64 (per-cell scalar rules made this phase 8.7 k cycles per pass, a fifth of
-        //      the kernel).  The position's words were fetched while the previous pass was still running ----
+    // Planes of one position -> channels 0..15 of its 81 rows of the planes buffer, by one warp: the legal mask is
+    // computed ONCE, by the warp (rules_warp.cuh), then lane writes cells lane, lane + 32, lane + 64 (per-cell scalar
+    // rules made this phase 8.7 k cycles per pass, a fifth of the kernel).
+    auto encode_position = [&](int g, int row) {
+        const uint32_t w = lane < 8 ? P.states[8 * (size_t)row + lane] : 0u;
+        uint32_t wd[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wd[k] = __shfl_sync(0xFFFFFFFFu, w, k);
+        const Pos p = unpack(wd);
+        uint32_t am[3], mm[3], oo[3];
+        int status;
+        warp_legal_mask<true>(p, lane, am, status, mm, oo);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int a = lane + 32 * q;
+            if (a < 81) {
+                const bool mine = (mm[q] >> lane) & 1u, occ = (oo[q] >> lane) & 1u, legal = (am[q] >> lane) & 1u;
+                const int r = (a * 57) >> 9, cc = a - 9 * r;
+                const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * 32u;
+                // bf16 1.0 = 0x3F80: planes mine, theirs | legal, ones; channels 4..15 are zero
+                *reinterpret_cast<uint4 *>(Pl + swz32(off)) =
+                    make_uint4((mine ? 0x3F80u : 0u) | ((occ && !mine) ? 0x3F800000u : 0u), (legal ? 0x3F80u : 0u) | 0x3F800000u, 0u, 0u);
+                *reinterpret_cast<uint4 *>(Pl + swz32(off + 16)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    };
+    // dense planes (tc_forward_obs_dev): consecutive threads write consecutive rows of one tile
+    auto encode_dense = [&](int pos0, int G, int tid, int nthreads) {
+        for (int idx = tid; idx < G * 81; idx += nthreads) {
+            const int cc = idx / (9 * G), gr = idx - 9 * G * cc;
+            const int g = gr / 9, r = gr - 9 * g;
+            const int a = 9 * r + cc;
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = c < P.in_planes ? P.obs[((size_t)(pos0 + g) * P.in_planes + c) * 81 + a] : 0.f;
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+            o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+            o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+            o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+            const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * 32u;
+            *reinterpret_cast<uint4 *>(Pl + swz32(off)) = o0;
+            *reinterpret_cast<uint4 *>(Pl + swz32(off + 16)) = o1;
+        }
+    };
+
+    // ---- planes of the first pass: every warp helps ----
+    {
+        const int G0 = min(GMAX, p_end - p_begin);
         if (P.states) {
-            if (warp < G) {
-                uint32_t wd[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) wd[k] = __shfl_sync(0xFFFFFFFFu, state_word, k);
-                const Pos p = unpack(wd);
-                uint32_t am[3], mm[3], oo[3];
-                int status;
-                warp_legal_mask<true>(p, lane, am, status, mm, oo);
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int a = lane + 32 * q;
-                    if (a < 81) {
-                        const bool mine = (mm[q] >> lane) & 1u, occ = (oo[q] >> lane) & 1u, legal = (am[q] >> lane) & 1u;
-                        const int r = (a * 57) >> 9, cc = a - 9 * r;
-                        const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * warp + r) * (uint32_t)SW;
-                        // bf16 1.0 = 0x3F80: planes mine, theirs | legal, ones; channels 4..15 are zero
-                        *reinterpret_cast<uint4 *>(Y + swz(off)) =
-                            make_uint4((mine ? 0x3F80u : 0u) | ((occ && !mine) ? 0x3F800000u : 0u), (legal ? 0x3F80u : 0u) | 0x3F800000u, 0u, 0u);
-                        *reinterpret_cast<uint4 *>(Y + swz(off + 16)) = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                }
-            }
-            // next pass: start the fetch now, use it after this pass's layers
-            if (pos0 + GMAX + warp < p_end && lane < 8) state_word = P.states[8 * (size_t)(pos0 + GMAX + warp) + lane];
+            if (warp < G0) encode_position(warp, p_begin + warp);
         } else {
-            // dense planes: consecutive threads write consecutive rows of one tile (64 bytes apart: conflict-free 16-byte
-            // stores); cells of one board row live 8 KB apart and would all fall on the same banks
-            for (int idx = threadIdx.x; idx < G * 81; idx += THREADS) {
-                const int cc = idx / (9 * G), gr = idx - 9 * G * cc;
-                const int g = gr / 9, r = gr - 9 * g;
-                const int a = 9 * r + cc;
-                float v[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) v[c] = c < P.in_planes ? P.obs[((size_t)(pos0 + g) * P.in_planes + c) * 81 + a] : 0.f;
-                uint4 o0, o1;
-                o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
-                o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
-                o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
-                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-                const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * (uint32_t)SW;
-                *reinterpret_cast<uint4 *>(Y + swz(off)) = o0;
-                *reinterpret_cast<uint4 *>(Y + swz(off + 16)) = o1;
-            }
+            encode_dense(p_begin, G0, (int)threadIdx.x, THREADS);
         }
         fence_async_smem();
         __syncthreads();
-        if (marks && pass < 4) marks[3 + 2 * pass] = clock64();
-        if (marks2 && pass == 0 && lane == 0 && warp < 8) marks2[100 + warp] = clock64();
+        if (marks) marks[3] = clock64();
+    }
 
-        // Layers are not separated by a block-wide barrier: input tile i of layer l+1 needs the activations of output
-        // tile i of layer l and the accumulator blocks of output tiles i-1, i, i+1 drained, nothing else.  Every role
-        // walks the layers of the pass on its own (lc = layers executed so far by this CTA: mbarrier phases); the issuer's
-        // whole walk sits inside ONE elected region - re-electing and re-converging the warp per layer cost ~600 cycles
-        // per layer.  Layer 0: planes(Y) -> X;  odd l (first conv of a block): X -> Y;  even l > 0: Y -> X, + residual X.
-        if (warp == 0) {
-            if (lane == 0) {
+    // From here on there is no block-wide barrier until the kernel ends.  The passes and their layers form ONE stream:
+    // input tile i of a layer needs the activations of output tile i of the layer before it and the accumulator blocks
+    // of output tiles i-1, i, i+1 drained and re-initialised, nothing else - and the stem of pass p+1 follows the last
+    // layer of pass p in exactly that way, its planes having been encoded into their own buffer by warps 2-3 while pass
+    // p was running.  Every role walks the stream on its own (lc = layers executed so far: the mbarrier phases); the
+    // issuer's whole walk sits inside ONE elected region - re-electing and re-converging the warp per layer cost ~600
+    // cycles per layer.  Layer 0: planes -> X;  odd l (first conv of a block): X -> Y;  even l > 0: Y -> X, + residual X.
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int pass = 0; pass < n_pass; ++pass)
                 for (int l = 0; l < n_layers; ++l) {
-                    const uint32_t lc = lcount + (uint32_t)l;
+                    const uint32_t lc = (uint32_t)(pass * n_layers + l);
                     if (l == n_layers - 1 && pass == n_pass - 1) griddep_launch(P.pdl_trigger == 2);
                     const bool more_layers = l + 1 < n_layers;
                     const bool more_passes = pass + 1 < n_pass;
@@ -342,7 +367,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
                         const uint32_t nb = (lc & 1u) ^ 1u;
                         uint8_t *Wn = W + nb * W_BUF;
                         if (lc >= 1) mbar_wait(wfree + nb, ((lc - 1) >> 1) & 1u);
-                        if (marks2 && pass == 0) marks2[21 + 6 * l] = clock64();
                         if (more_layers) {
                             mbar_expect_tx(wfull + nb, 3u * W_DY);
                             for (int dy = 0; dy < 3; ++dy) tma_load_2d(Wn + dy * W_DY, &tmW_conv, wfull + nb, 0, (l * 3 + dy) * N3);
@@ -352,42 +376,64 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
                         }
                     }
                 }
-            }
-        } else if (warp == 1) {
-            if (elect_one()) {
-                const uint32_t base4 = smem_u32(smem) >> 4;
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t base4 = smem_u32(smem) >> 4;
+            for (int pass = 0; pass < n_pass; ++pass) {
+                if (marks2 && pass < 4) marks2[150 + pass] = clock64();
                 for (int l = 0; l < n_layers; ++l) {
-                    const uint32_t lc = lcount + (uint32_t)l;
+                    const uint32_t lc = (uint32_t)(pass * n_layers + l);
                     const uint32_t wb = lc & 1u;
-                    if (marks2 && pass == 0) marks2[20 + 6 * l] = clock64();
-                    if (l == 0) mbar_wait(wfull + wb, (lc >> 1) & 1u);        // later layers: waited for inside the layer before
+                    if (lc == 0) mbar_wait(wfull + wb, 0u);              // later layers: waited for inside the layer before
+                    if (l == 0 && pass > 0) mbar_wait(pready, (uint32_t)(pass - 1) & 1u);
                     tc_fence_after();
-                    if (marks2 && pass == 0) marks2[16 + 6 * l] = clock64();
+                    if (marks2 && lc < 18) marks2[16 + 6 * lc] = clock64();
                     uint64_t *prev = aready + ((lc - 1) & 1u) * BAR_STRIDE;
                     const uint32_t pph = ((lc - 1) >> 1) & 1u;
-                    uint64_t *nwf = l + 1 < n_layers ? wfull + (wb ^ 1u) : nullptr;
+                    uint64_t *nwf = (l + 1 < n_layers || pass + 1 < n_pass) ? wfull + (wb ^ 1u) : nullptr;
                     const uint32_t nwph = ((lc + 1) >> 1) & 1u;
                     if (l == 0) {
-                        if (wb) issue_layer<0, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph);
-                        else issue_layer<0, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph);
+                        if (wb) issue_layer<0, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph, lc == 0, pfree);
+                        else issue_layer<0, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph, lc == 0, pfree);
                     } else if (l & 1) {
-                        if (wb) issue_layer<1, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph);
-                        else issue_layer<1, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph);
+                        if (wb) issue_layer<1, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph, false, pfree);
+                        else issue_layer<1, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph, false, pfree);
                     } else {
-                        if (wb) issue_layer<2, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph);
-                        else issue_layer<2, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph);
+                        if (wb) issue_layer<2, 1>(base4, tmem_base, tdone, prev, pph, wfree + 1, nwf, nwph, false, pfree);
+                        else issue_layer<2, 0>(base4, tmem_base, tdone, prev, pph, wfree, nwf, nwph, false, pfree);
                     }
-                    if (marks2 && pass == 0) marks2[17 + 6 * l] = clock64();
+                    if (marks2 && lc < 18) marks2[17 + 6 * lc] = clock64();
                 }
             }
-        } else if (warp >= FIRST_EPI) {
-            // ===== epilogue: (+ residual) ReLU, bf16 pack, store; the drained block gets the bias of its next use =====
-            const int quarter = warp & 3, egroup = (warp - FIRST_EPI) >> 2;
-            const int i = 32 * quarter + lane;                       // lane of every tile = (position, board row)
-            const int g = i / PITCH, r = i - PITCH * g;
+        }
+    } else if (warp < FIRST_EPI) {
+        // ===== planes of pass p >= 1, while pass p-1 runs: once the stem of pass p-1 has been consumed by the tensor pipe
+        //       the planes buffer is free (a barrier of its own: a parity wait cannot skip phases of a shared one) =====
+        for (int pass = 1; pass < n_pass; ++pass) {
+            mbar_wait(pfree, (uint32_t)(pass - 1) & 1u);
+            const int pos0 = p_begin + pass * GMAX;
+            const int G = min(GMAX, p_end - pos0);
+            if (P.states) {
+                for (int g = warp - 2; g < G; g += FIRST_EPI - 2) encode_position(g, pos0 + g);
+            } else {
+                encode_dense(pos0, G, (int)threadIdx.x - 64, 32 * (FIRST_EPI - 2));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pready);
+        }
+    } else {
+        // ===== epilogue: (+ residual) ReLU, bf16 pack, store; the drained block gets the bias of its next use =====
+        const int quarter = warp & 3, egroup = (warp - FIRST_EPI) >> 2;
+        const int i = 32 * quarter + lane;                       // lane of every tile = (position, board row)
+        const int g = i / PITCH, r = i - PITCH * g;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int pos0 = p_begin + pass * GMAX;
+            const int G = min(GMAX, p_end - pos0);
             const bool valid = g < G && r < 9;
             for (int l = 0; l < n_layers; ++l) {
-                const uint32_t lc = lcount + (uint32_t)l;
+                const uint32_t lc = (uint32_t)(pass * n_layers + l);
                 uint8_t *dst = (l & 1) ? Y : X;
                 const bool residual = l > 0 && !(l & 1);             // second conv of a block: + the block's input, in X
                 const bool last = l == n_layers - 1;
@@ -428,9 +474,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
                             ov.y = relu_pack(acc[c + 2], acc[c + 3], zero2);
                             ov.z = relu_pack(acc[c + 4], acc[c + 5], zero2);
                             ov.w = relu_pack(acc[c + 6], acc[c + 7], zero2);
-                            // the fc1 input is column-major per position ([row][board column][board row][C], the K
-                            // order fc1's weights are uploaded in for this kernel): the nine rows of a position's column
-                            // are 576 contiguous bytes, written by nine adjacent lanes
+                            // The fc1 input is column-major per position ([row][board column][board row][C], the K order
+                            // fc1's weights are uploaded in for this kernel): the nine rows of a position's column are 576
+                            // contiguous bytes, written by nine adjacent lanes.  (The 62 KB a pass writes leave every SM in
+                            // the same 2 k cycles; sending them through shared memory and the TMA engine instead - 576-byte
+                            // bulk copies - was measured slower, 44.4 vs 45.1 M sims/s.)
                             if (last) *reinterpret_cast<uint4 *>(P.out + ((size_t)(pos0 + g) * 81 + 9 * j + r) * C + c) = ov;
                             else *cell = ov;
                         }
@@ -442,16 +490,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(aready + (lc & 1u) * BAR_STRIDE + j);
-                    if (marks2 && pass == 0 && warp == FIRST_EPI && lane == 0) marks2[(j == 0 ? 18 : 19) + 6 * l] = clock64();
+                    if (marks2 && lc < 18 && warp == FIRST_EPI && lane == 0) marks2[(j == 0 ? 18 : 19) + 6 * lc] = clock64();
                 }
             }
         }
-        lcount += (uint32_t)n_layers;
-        // pass boundary: the next pass's planes overwrite Y and its stem overwrites the accumulators
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (marks && pass < 4) marks[4 + 2 * pass] = clock64();
     }
     tc_fence_before();
     __syncthreads();
@@ -459,7 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     if (marks) { marks[11] = clock64(); marks[12] = n_pass; marks[13] = p_end - p_begin; }
 }
 
-static size_t smem_bytes() { return 1024 + 2 * (size_t)BUF_BYTES + 2 * (size_t)W_BUF + (3 * BAR_STRIDE + 4) * 8 + 16; }
+static size_t smem_bytes() { return 1024 + 2 * (size_t)BUF_BYTES + 2 * (size_t)W_BUF + PBUF_BYTES + (3 * BAR_STRIDE + 6) * 8 + 16; }
 
 }  // namespace col
 
@@ -494,7 +536,7 @@ int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const
     P.pdl_trigger = pdl_trigger_enabled();
     static long long *timeline_dev = nullptr;
     if (getenv("TACULT_FUSED_TIMELINE")) {
-        if (!timeline_dev) { cudaMalloc(&timeline_dev, 128 * sizeof(long long)); cudaMemset(timeline_dev, 0, 128 * sizeof(long long)); }
+        if (!timeline_dev) { cudaMalloc(&timeline_dev, 160 * sizeof(long long)); cudaMemset(timeline_dev, 0, 160 * sizeof(long long)); }
         P.timeline = timeline_dev;
     }
     const size_t smem = col::smem_bytes();
@@ -508,24 +550,19 @@ int launch_trunk_col(const CUtensorMap &w_stem, const CUtensorMap &w_conv, const
     }
     TC_CUDA(launch_chain(col::k_trunk_col, grid, col::THREADS, smem, st, w_stem, w_conv, P));
     if (P.timeline) {
-        long long m[128];
+        long long m[160];
         cudaStreamSynchronize(st);
         cudaMemcpy(m, timeline_dev, sizeof m, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[col marks] CTA 0, %lld positions in %lld passes; cycles since kernel entry: prologue done %lld | "
-                "dependency wait over %lld | pass 0 planes %lld done %lld | pass 1 planes %lld done %lld | exit %lld\n",
-                m[13], m[12], m[1] - m[0], m[2] - m[0], m[3] - m[0], m[4] - m[0], m[12] > 1 ? m[5] - m[0] : 0,
-                m[12] > 1 ? m[6] - m[0] : 0, m[11] - m[0]);
-        fprintf(stderr, "[col layers] pass 0, per layer: issuer at the weights barrier | issue start | issue end | epilogue of tile 0 | of tile 8 (cycles since kernel entry)\n");
-        for (int l = 0; l <= n_conv && l < 11; ++l)
-            fprintf(stderr, "[col layers] %2d: %7lld %7lld %7lld %7lld %7lld\n", l, m[20 + 6 * l] - m[0], m[16 + 6 * l] - m[0],
-                    m[17 + 6 * l] - m[0], m[18 + 6 * l] - m[0], m[19 + 6 * l] - m[0]);
-        fprintf(stderr, "[col layers] warps 0..7 after the planes barrier:");
-        for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld", m[100 + w] - m[0]);
-        fprintf(stderr, " | at the top of layer 0:");
-        for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld", m[108 + w] - m[0]);
-        fprintf(stderr, "\n[col layers] TMA of the next layer's weights issued at:");
-        for (int l = 0; l <= n_conv && l < 11; ++l) fprintf(stderr, " %lld", m[21 + 6 * l] - m[0]);
-        fprintf(stderr, "\n");
+                "dependency wait over %lld | planes of pass 0 done %lld | issuer starts pass 0 at %lld, pass 1 at %lld, pass 2 at %lld | "
+                "exit %lld\n",
+                m[13], m[12], m[1] - m[0], m[2] - m[0], m[3] - m[0], m[150] - m[0], m[12] > 1 ? m[151] - m[0] : 0,
+                m[12] > 2 ? m[152] - m[0] : 0, m[11] - m[0]);
+        fprintf(stderr, "[col layers] layer of the stream: issue start | issue end | this group's epilogue of tile 0 | of its last tile "
+                "(cycles since kernel entry)\n");
+        for (int l = 0; l < (int)m[12] * (n_conv + 1) && l < 18; ++l)
+            fprintf(stderr, "[col layers] %2d: %7lld %7lld %7lld %7lld\n", l, m[16 + 6 * l] - m[0], m[17 + 6 * l] - m[0],
+                    m[18 + 6 * l] - m[0], m[19 + 6 * l] - m[0]);
     }
     return TC_OK;
 }

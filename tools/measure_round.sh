@@ -3,7 +3,7 @@
 # commands under ncu.  Outputs land in gpurun_out/; tools/ncu_summary.py turns them into profiles/*.json here.
 set -u
 mkdir -p gpurun_out
-TAG=${1:-r02_final}
+TAG=${1:-r02_final2}
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
 timeout 900 python bench.py > gpurun_out/bench_$TAG.log 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; echo "reference arm rc=$?"
@@ -16,7 +16,7 @@ timeout 200 $SHORT > gpurun_out/plain_short_$TAG.log 2>&1; echo "short plain rc=
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv \
     $SHORT > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launch list rc=$?"
 # one full capture per hot kernel (skip the warm-up launches)
-for K in k_trunk_fused k_backup_select k_fc1_heads; do
+for K in k_trunk_col k_backup_select k_fc1_heads; do
   timeout 900 ncu --set full --import-source on --clock-control none -k regex:$K -s 300 -c 1 -f -o gpurun_out/prof_${K}_$TAG \
       $SHORT > gpurun_out/ncu_${K}_$TAG.log 2>&1; echo "ncu $K rc=$?"
 done
