@@ -685,9 +685,10 @@ def roofline(prof, k0, k1, a, evaluator, flops_eval):
             "algorithmic_flops_per_leaf": trunk_flops_per_leaf if top == "nn_conv" else None}
     if top == "nn_conv":
         # measured with tools/probes/umma_rate_probe.cu: a 128 x N x 16 UMMA costs max((4096 + 32 N) / 128, N / 2) cycles, i.e.
-        # at N = 32 channels the tensor pipe is fed by shared-memory operand reads at 128 B/clk, not by its math rate
-        roof["note"] = ("operand-fetch bound at 32 channels: 40 cycles per UMMA for 16 cycles of math; the kernel runs at "
-                        "about 82 % of that shared-memory bound (DESIGN.md section 4)")
+        # the tensor pipe of a 32-channel net is fed by shared-memory operand reads at 128 B/clk, not by its math rate
+        roof["note"] = ("column-tiled trunk k_trunk_col: the three horizontal taps stacked in N (6 UMMAs of N = 96 per tile and layer "
+                        "instead of 18 + 3 of N = 32); bound by shared-memory bandwidth - 42 KB of operand fetch + 8-16 KB of epilogue "
+                        "rows per tile and layer through 128 B/clk = 390-450 cycles, measured 428 (DESIGN.md section 4)")
     return roof, kernels
 
 

@@ -89,7 +89,11 @@ __device__ __forceinline__ void griddep_launch(int on)
 
 inline int pdl_trigger_enabled()
 {
-    static const int on = [] { const char *v = getenv("TACULT_PDL_TRIGGER"); return v ? atoi(v) : 0; }();
+    // 3: only the tree kernels trigger their dependents at entry - the trunk's CTAs, which need a whole SM, become resident
+    // as the descent's last trees finish and run their prologue (shared-memory set-up, TMEM allocation, weight TMA) behind
+    // that tail.  Every kernel launched with the programmatic attribute calls griddep_wait() before it reads anything a
+    // predecessor wrote.
+    static const int on = [] { const char *v = getenv("TACULT_PDL_TRIGGER"); return v ? atoi(v) : 3; }();
     return on;
 }
 
@@ -97,6 +101,24 @@ inline bool pdl_enabled()
 {
     static const int on = [] { const char *v = getenv("TACULT_PDL"); return v ? atoi(v) : 1; }();
     return on != 0;
+}
+
+// TACULT_CARVEOUT=1: every kernel of the simulation chain asks for the maximum shared-memory carve-out, so that an SM does
+// not have to re-partition its L1 / shared memory between the tree kernels (no shared memory) and the network kernels
+// (87 - 228 KB) four times per simulation.
+inline int carveout_enabled()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("TACULT_CARVEOUT");
+        on = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return on;
+}
+template <typename K>
+inline void prefer_max_shared(K kernel)
+{
+    if (carveout_enabled()) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 template <typename... KArgs, typename... Args>

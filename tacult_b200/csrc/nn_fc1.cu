@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(THREADS) k_fc1_heads(const __grid_constant__ C
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2);
     int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
-    griddep_launch(P.pdl_trigger == 1);
+    griddep_launch(P.pdl_trigger == 1 || P.pdl_trigger == 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long *mk = (P.marks && threadIdx.x == 64 && (blockIdx.x & 1) == 0 && (blockIdx.x >> 1) < 256)
                         ? P.marks + 16 * (blockIdx.x >> 1) : nullptr;
@@ -502,6 +502,7 @@ int launch_fc1_heads(const CUtensorMap &a, const CUtensorMap &b, const CUtensorM
     TC_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         TC_CUDA(cudaFuncSetAttribute(fc1::k_fc1_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        prefer_max_shared(fc1::k_fc1_heads);
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};

@@ -29,6 +29,7 @@
 #include "nn_bf16.cuh"
 #include "nn_fused.cuh"
 #include "rules.cuh"
+#include "rules_warp.cuh"
 #include "tcgen05.cuh"
 
 namespace tc {
@@ -192,32 +193,40 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_trunk_fused(const __grid_c
         const int T = (100 * G + 127) / 128;
         // ---- observation planes of the group -> channels 0..15 of the group's rows in Y (activation layout:
         //      the stem's UMMAs read K = 16 of it; pad rows are never touched and stay zero) ----
-        if (warp > ISSUERS) {
+        if (warp > ISSUERS && P.states) {
+            // one warp per position: the legal mask is computed ONCE, by the warp (rules_warp.cuh), then lane writes the
+            // cells lane, lane + 32, lane + 64 (the per-cell scalar rules this replaced took 8 k cycles per group)
+            for (int g = warp - 1 - ISSUERS; g < G; g += EPI_WARPS) {
+                const uint32_t w = lane < 8 ? P.states[8 * (size_t)(pos0 + g) + lane] : 0u;
+                uint32_t wd[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wd[k] = __shfl_sync(0xFFFFFFFFu, w, k);
+                const Pos p = unpack(wd);
+                uint32_t am[3], mm[3], oo[3];
+                int status;
+                warp_legal_mask<true>(p, lane, am, status, mm, oo);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int a = lane + 32 * q;
+                    if (a < 81) {
+                        const bool mine = (mm[q] >> lane) & 1u, occ = (oo[q] >> lane) & 1u, legal = (am[q] >> lane) & 1u;
+                        const int r = (a * 57) >> 9, cc = a - 9 * r;
+                        const uint32_t off = (uint32_t)(LEAD + 100 * g + 10 * r + cc) * (uint32_t)SW;
+                        // bf16 1.0 = 0x3F80: planes mine, theirs | legal, ones; channels 4..15 are zero
+                        *reinterpret_cast<uint4 *>(Y + swz<SW>(off)) =
+                            make_uint4((mine ? 0x3F80u : 0u) | ((occ && !mine) ? 0x3F800000u : 0u), (legal ? 0x3F80u : 0u) | 0x3F800000u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(Y + swz<SW>(off + 16)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+            }
+            fence_async_smem();
+        } else if (warp > ISSUERS) {
             for (int idx = threadIdx.x - 32 * (1 + ISSUERS); idx < G * 81; idx += 32 * EPI_WARPS) {
                 const int g = idx / 81, a = idx - 81 * g;
                 const int row = pos0 + g;
                 float v[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) v[c] = 0.f;
-                if (row < count) {
-                    if (P.states) {
-                        uint32_t wd[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) wd[k] = P.states[8 * (size_t)row + k];
-                        Pos p = unpack(wd);
-                        uint32_t lw[3];
-                        legal_words(p, summarize(p), lw);
-                        const bool mine = action_bit(p.mine, a), occ = action_bit(p.occ, a);
-                        v[0] = mine ? 1.f : 0.f;
-                        v[1] = (occ && !mine) ? 1.f : 0.f;
-                        v[2] = action_bit(lw, a) ? 1.f : 0.f;
-                        v[3] = 1.f;
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            if (c < P.in_planes) v[c] = P.obs[((size_t)row * P.in_planes + c) * 81 + a];
-                    }
-                }
+                for (int c = 0; c < 16; ++c) v[c] = (row < count && c < P.in_planes) ? P.obs[((size_t)row * P.in_planes + c) * 81 + a] : 0.f;
                 uint4 o0, o1;
                 o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
                 o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);

@@ -679,7 +679,7 @@ __device__ __forceinline__ void expand_backup_tree(const TreeStore &ts, const in
 
 __global__ void __launch_bounds__(128, 7) k_select(TreeStore ts, double cpuct)
 {
-    griddep_launch(ts.pdl_trigger == 1);
+    griddep_launch(ts.pdl_trigger == 1 || ts.pdl_trigger == 3);
     griddep_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && ts.eval_count_next) *ts.eval_count_next = 0;
     const int tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(TreeStore ts)
 // expansion/backup, then walks down again while the path's nodes are still in cache.
 __global__ void __launch_bounds__(128, 7) k_backup_select(TreeStore ts, double cpuct)
 {
-    griddep_launch(ts.pdl_trigger == 1);
+    griddep_launch(ts.pdl_trigger == 1 || ts.pdl_trigger == 3);
     griddep_wait();
     // the other counter of the pair was last read by the evaluator kernels of the previous simulation, which have
     // completed; the next simulation's descent starts counting from zero without a memset node in the stream
@@ -819,16 +819,19 @@ void launch_advance(const TreeStore &ts, const int8_t *actions_dev, int restart,
 
 void launch_select(const TreeStore &ts, double cpuct, cudaStream_t st)
 {
+    prefer_max_shared(k_select);
     launch_chain(k_select, warp_grid(ts.E, 128), 128, 0, st, ts, cpuct);
 }
 
 void launch_backup_select(const TreeStore &ts, double cpuct, cudaStream_t st)
 {
+    prefer_max_shared(k_backup_select);
     launch_chain(k_backup_select, warp_grid(ts.E, 128), 128, 0, st, ts, cpuct);
 }
 
 void launch_expand_backup(const TreeStore &ts, cudaStream_t st)
 {
+    prefer_max_shared(k_expand_backup);
     launch_chain(k_expand_backup, warp_grid(ts.E, 128), 128, 0, st, ts);
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Counts the Blackwell-only SASS mnemonics per kernel of libtacult_b200.so (evidence that the tensor-core kernels are
 tcgen05 / TMEM / TMA code, not mma.sync or library calls):  UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA load,
-UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM alloc.   python tools/sass_ops.py > profiles/sass_ops.txt"""
+UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM alloc, STTM = tcgen05.st.   python tools/sass_ops.py > profiles/sass_ops.txt"""
 import collections
 import os
 import re
@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 LIB = os.path.join(ROOT, "tacult_b200", "lib", "libtacult_b200.so")
-OPS = ["UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "UTCATOMSWS", "SYNCS", "REDUX", "HMMA", "DFMA", "DMUL", "MUFU.RSQ64H"]
+OPS = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCBAR", "UTCATOMSWS", "SYNCS", "REDUX", "HMMA", "DFMA", "DMUL", "MUFU.RSQ64H"]
 
 
 def main():
