@@ -703,6 +703,7 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
     counts_buf = torch.zeros((E, 81), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     next_buf = torch.zeros((E, 8), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     status_buf = torch.zeros((E,), dtype=torch.int8).pin_memory().numpy()
+    acts_buf = torch.zeros((E,), dtype=torch.int8).pin_memory().numpy()
     # staggered synthetic positions: random legal moves to a random depth below 50 plies
     depth = rng.randint(0, 50, size=E)
     ply_no = np.zeros(E, dtype=np.int64)
@@ -727,14 +728,10 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
         eng.set_roots_packed(states)
         eng.search(sims, CPUCT)
         counts = eng.root_counts(out=counts_buf)
+        # host move choice, one C call (tc_choose_actions): tau = 1 -> a ~ counts / sum (coach.py:140), tau = 0 -> arg-max
         tau_one = (ply_no + 1) < TEMP_THRESHOLD
-        acts = counts.argmax(1)                                     # tau = 0: arg-max (lowest index on ties)
-        rows = np.flatnonzero(tau_one)
-        if rows.size:                                               # tau = 1: a ~ counts / sum (coach.py:140)
-            cum = np.cumsum(counts[rows], axis=1, dtype=np.int64)
-            draw = (rng.random_sample(rows.size) * cum[:, -1]).astype(np.int64)
-            acts[rows] = (cum > draw[:, None]).argmax(1)
-        nxt, st = tb.rules_step(states, acts.astype(np.int8), out=next_buf, status=status_buf)
+        acts = tb.choose_actions(counts, tau_one, rng.random_sample(E), out=acts_buf)
+        nxt, st = tb.rules_step(states, acts, out=next_buf, status=status_buf)
         states[:] = nxt
         ply_no[:] += 1
         done = np.flatnonzero(st != 0)         # finished games: fresh trees (VectorizedMCTS.reset), initial position

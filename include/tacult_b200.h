@@ -150,6 +150,13 @@ void tc_gs_obs(const tc_gamestate *s, float *obs324);              /* .get_obs  
 /* the canonicalBoards list of getActionProbs (mcts.py:175) -> packed roots in one call; active[i] == 0 on entry marks a
  * None board (mcts.py:235-239); finished boards whose side is not +1 (arena.py:176-184) come back inactive */
 int  tc_gs_pack(int n, const tc_gamestate *gs_host, uint32_t *states_host, uint8_t *active_host);
+/* The actor's move choice from the root visit counts of tc_root_counts, on the host, one call for all envs
+ * (base/coach.py:125,131,140: temps = episodeStep < tempThreshold, pi = getActionProbs(...), action = np.random.choice(81, p=pi);
+ * base/mcts.py:200-214: tau = 1 -> pi = counts / sum, tau = 0 -> the arg-max).  counts_host u32[n][81]; tau_one u8[n] (1: sample
+ * a ~ counts / sum with the caller's uniform u[i] in [0,1): the first action whose cumulative count exceeds floor(u * sum);
+ * 0: arg-max, lowest index on ties); actions_host i8[n].  A row of zeros (finished env) gives action 0. */
+int  tc_choose_actions(int n, const uint32_t *counts_host, const uint8_t *tau_one_host, const double *u_host,
+                       int8_t *actions_host);
 
 /* ---- search engine: replaces VectorizedMCTS (/root/reference/src/tacult/base/mcts.py:147-358) ---- */
 int tc_create(const tc_config *cfg, tc_engine **out);              /* VectorizedMCTS.__init__ mcts.py:152-162 */

@@ -131,6 +131,7 @@ SYMBOLS = {
     "tc_gs_terminal_value": (_i, [_gsp]),
     "tc_gs_obs": (None, [_gsp, _vp]),
     "tc_gs_pack": (_i, [_i, _vp, _vp, _vp]),
+    "tc_choose_actions": (_i, [_i, _vp, _vp, _vp, _vp]),
     "tc_rules_step": (_i, [_i, _vp, _vp, _vp, _vp]),
     "tc_rules_legal_mask": (_i, [_i, _vp, _vp]),
     "tc_rules_status": (_i, [_i, _vp, _vp]),

@@ -137,3 +137,32 @@ extern "C" int tc_gs_pack(int n, const tc_gamestate *gs_host, uint32_t *states_h
     }
     return TC_OK;
 }
+
+// Move choice from visit counts (coach.py:125-140, mcts.py:200-214): see the header.  Equals, draw for draw, the numpy
+// formulation  cum = cumsum(counts); a = argmax(cum > floor(u * cum[-1]))  /  counts.argmax()  that bench.py used before.
+extern "C" int tc_choose_actions(int n, const uint32_t *counts_host, const uint8_t *tau_one_host, const double *u_host,
+                                 int8_t *actions_host)
+{
+    TC_CHECK(n >= 0 && (n == 0 || (counts_host && tau_one_host && actions_host)), TC_EINVAL, "tc_choose_actions: null buffer");
+    for (int i = 0; i < n; ++i) {
+        const uint32_t *c = counts_host + 81 * (size_t)i;
+        int best = 0;
+        if (tau_one_host[i]) {
+            TC_CHECK(u_host != nullptr, TC_EINVAL, "tc_choose_actions: tau = 1 rows need uniform draws");
+            int64_t total = 0;
+            for (int a = 0; a < 81; ++a) total += c[a];
+            const int64_t draw = (int64_t)(u_host[i] * (double)total);
+            int64_t cum = 0;
+            for (int a = 0; a < 81; ++a) {
+                cum += c[a];
+                if (cum > draw) { best = a; break; }
+            }
+        } else {
+            uint32_t top = c[0];
+            for (int a = 1; a < 81; ++a)
+                if (c[a] > top) { top = c[a]; best = a; }
+        }
+        actions_host[i] = (int8_t)best;
+    }
+    return TC_OK;
+}

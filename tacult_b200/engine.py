@@ -247,6 +247,24 @@ class Engine:
             ctypes.c_void_p(int(pi_dev_ptr)), ctypes.c_void_p(int(z_dev_ptr))))
 
 
+def choose_actions(counts, tau_one, u=None, out=None):
+    """The actor's move choice for every env in one host call (tc_choose_actions; coach.py:125-140): rows with tau_one
+    sample a ~ counts / sum using the caller's uniform draws u[i], the others take the arg-max (lowest index on ties)."""
+    lib = _lib.load()
+    counts = np.ascontiguousarray(counts, dtype=np.uint32).reshape(-1, 81)
+    n = counts.shape[0]
+    tau = np.ascontiguousarray(tau_one, dtype=np.uint8).reshape(-1)
+    assert tau.shape[0] == n
+    if u is not None:
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+        assert u.shape[0] == n
+    if out is None:
+        out = np.empty(n, dtype=np.int8)
+    assert out.shape == (n,) and out.dtype == np.int8
+    check(lib.tc_choose_actions(n, ptr(counts), ptr(tau), ptr(u), ptr(out)))
+    return out
+
+
 # -- stateless rules hooks ---------------------------------------------------------------------
 def rules_step(states, actions, out=None, status=None):
     """out / status: optional caller-owned (e.g. pinned) result buffers u32[n, 8] / i8[n]."""

@@ -170,3 +170,28 @@ def test_vectorised_action_probs_equal_the_per_env_loop_draw_for_draw():
         state_got = np.random.get_state()
         assert np.array_equal(want, got, equal_nan=True)
         assert np.array_equal(state_want[1], state_got[1]) and state_want[2] == state_got[2]
+
+
+def test_choose_actions_equals_the_numpy_formulation():
+    """tc_choose_actions (the actor's move choice, coach.py:125-140) against cumsum / arg-max in numpy, draw for draw,
+    including zero rows (finished envs), single-action rows and exact ties."""
+    from tacult_b200.engine import choose_actions
+    rng = np.random.RandomState(3)
+    counts = rng.randint(0, 40, size=(3000, 81)).astype(np.uint32)
+    counts[rng.random_sample(counts.shape) < 0.6] = 0
+    counts[::11] = 0
+    counts[5::11, :] = 0
+    counts[5::11, 17] = 200
+    counts[7::13, :] = 3                                    # ties everywhere: the lowest index wins at tau = 0
+    tau = rng.randint(0, 2, 3000).astype(bool)
+    u = rng.random_sample(3000)
+    u[:50] = np.nextafter(1.0, 0.0)                          # the largest draw still picks a visited action
+    want = counts.argmax(1)
+    cum = np.cumsum(counts, axis=1, dtype=np.int64)
+    draw = (u * cum[:, -1]).astype(np.int64)
+    want = np.where(tau, (cum > draw[:, None]).argmax(1), want)
+    got = choose_actions(counts, tau, u)
+    assert got.dtype == np.int8 and np.array_equal(got, want)
+    sampled = tau & (cum[:, -1] > 0)
+    assert (counts[np.flatnonzero(sampled), got[sampled]] > 0).all()
+    assert np.array_equal(choose_actions(counts, np.zeros(3000, bool)), counts.argmax(1))      # u not needed at tau = 0
