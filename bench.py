@@ -704,21 +704,29 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
     next_buf = torch.zeros((E, 8), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     status_buf = torch.zeros((E,), dtype=torch.int8).pin_memory().numpy()
     acts_buf = torch.zeros((E,), dtype=torch.int8).pin_memory().numpy()
-    # staggered synthetic positions: random legal moves to a random depth below 50 plies
-    depth = rng.randint(0, 50, size=E)
-    ply_no = np.zeros(E, dtype=np.int64)
-    for d in range(50):
-        todo = np.flatnonzero(depth > d)
-        if todo.size == 0:
+    # Staggered synthetic positions spread over ALL game phases, the distribution the device-resident loop measures in
+    # (its envs have been auto-resetting for 150 plies): every env plays one random-move game to its end and starts from a
+    # uniformly random ply of it.  (Until round 2's last bench this was "random moves to a random depth below 50", which
+    # has no late-game positions: 3.6-3.9 k leaves per simulation instead of 3.0-3.3 k, i.e. beyond the 3552 leaves the
+    # trunk evaluates in two passes per SM - a different workload from the one `value` is quoted on.)
+    cur = np.zeros((E, 8), dtype=np.uint32)
+    hist = [cur.copy()]
+    alive = np.ones(E, dtype=bool)
+    length = np.zeros(E, dtype=np.int64)
+    for _ in range(81):
+        idx = np.flatnonzero(alive)
+        if idx.size == 0:
             break
-        mask = tb.rules_legal_mask(states[todo])
-        acts = np.array([rng.choice(np.flatnonzero(m)) if m.any() else -1 for m in mask], dtype=np.int8)
-        ok = acts >= 0
-        nxt, st = tb.rules_step(states[todo][ok], acts[ok])
-        keep = st == 0                          # do not step into finished games
-        idx = todo[ok][keep]
-        states[idx] = nxt[keep]
-        ply_no[idx] += 1
+        mask = tb.rules_legal_mask(cur[idx]).astype(bool)
+        acts = (rng.random_sample(mask.shape) * mask).argmax(1).astype(np.int8)      # a uniformly random legal move
+        nxt, st = tb.rules_step(cur[idx], acts)
+        cur[idx] = nxt
+        length[idx] += 1
+        alive[idx[st != 0]] = False
+        hist.append(cur.copy())
+    pick = (rng.random_sample(E) * length).astype(np.int64)          # a ply before the game's last move: never terminal
+    states[:] = np.stack(hist)[pick, np.arange(E)]
+    ply_no = pick.copy()
     eng.reset(-1)
     eng.reset_stats()
     h2d = E * 32 + E * 32 + E          # roots + positions and actions handed to tc_rules_step
@@ -743,6 +751,7 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
 
     for _ in range(a.warmup):
         one_ply()
+    k0 = eng.stats()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -752,11 +761,16 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     barrier()
+    k1 = eng.stats()
+    leaves_per_step = (k1["nn_leaves"] - k0["nn_leaves"]) / max(1, a.steps * sims)
     dt = reduce_scalar(dt, dist.ReduceOp.MAX if world > 1 else None)
     done = reduce_scalar(float(done), dist.ReduceOp.SUM if world > 1 else None)
     return {"value": done / dt, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": 1e3 * dt / a.steps, "path": "tc_set_roots_packed -> tc_search -> tc_root_counts -> host move "
-            "choice -> tc_rules_step, pinned host buffers"}
+            "choice (tc_choose_actions) -> tc_rules_step, pinned host buffers",
+            "positions": "every env starts from a uniformly random ply of a random-move game (all game phases, as in the "
+                         "device-resident loop); finished games restart from the initial position",
+            "leaf_evals_per_simulation_step": leaves_per_step}
 
 
 def main():

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-python bench.py --skip-cpu-baseline --skip-extras --steps 8 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2), d['e2e'])"
-timeout 600 python -m pytest tests/test_gpu_callers.py tests/test_gpu_selfplay.py -m gpu -x -q 2>&1 | tail -2
+python bench.py --skip-cpu-baseline --skip-extras --steps 8 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2), d['e2e'], d['roofline']['rows_per_launch'])"
