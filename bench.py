@@ -444,6 +444,29 @@ def full_iteration(eng, torch, stream, sims, seed, barrier, reduce_scalar, dist,
                      "(base/coach.py:160-193)"}
 
 
+def all_phase_positions(tb, rng, E):
+    """Staggered synthetic positions spread over ALL game phases, the distribution the device-resident loop measures in
+    (its envs have been auto-resetting for 150 plies): every env plays one random-move game to its end and starts from a
+    uniformly random ply of it.  Returns (packed states u32[E, 8], ply index per env)."""
+    cur = np.zeros((E, 8), dtype=np.uint32)
+    hist = [cur.copy()]
+    alive = np.ones(E, dtype=bool)
+    length = np.zeros(E, dtype=np.int64)
+    for _ in range(81):
+        idx = np.flatnonzero(alive)
+        if idx.size == 0:
+            break
+        mask = tb.rules_legal_mask(cur[idx]).astype(bool)
+        acts = (rng.random_sample(mask.shape) * mask).argmax(1).astype(np.int8)      # a uniformly random legal move
+        nxt, st = tb.rules_step(cur[idx], acts)
+        cur[idx] = nxt
+        length[idx] += 1
+        alive[idx[st != 0]] = False
+        hist.append(cur.copy())
+    pick = (rng.random_sample(E) * length).astype(np.int64)          # a ply before the game's last move: never terminal
+    return np.stack(hist)[pick, np.arange(E)], pick
+
+
 def run_dropin(a, eng, tb, torch, evaluator):
     """`tacult_b200.VectorizedMCTS.getActionProbs(list[GameState], temps)` — the call `Coach.executeEpisode` makes
     (coach.py:131) — on 4096 GameState objects x 200 sims: the timed span is the drop-in's own call (host packing of
@@ -464,17 +487,7 @@ def run_dropin(a, eng, tb, torch, evaluator):
                 tc_device=torch.cuda.current_device())
     mcts = tb.VectorizedMCTS(None, Net(), args)
     rng = np.random.RandomState(11)
-    depth = rng.randint(0, 40, size=E)
-    states = np.zeros((E, 8), dtype=np.uint32)
-    for d in range(40):                                   # staggered mid-game positions (live ones only)
-        todo = np.flatnonzero(depth > d)
-        if todo.size == 0:
-            break
-        mask = tb.rules_legal_mask(states[todo])
-        acts = np.array([rng.choice(np.flatnonzero(m)) for m in mask], dtype=np.int8)
-        nxt, st = tb.rules_step(states[todo], acts)
-        states[todo[st == 0]] = nxt[st == 0]
-    ply_no = np.zeros(E, dtype=np.int64)
+    states, ply_no = all_phase_positions(tb, rng, E)        # the same distribution as the `e2e` leg
     total_s, pack_s, n_timed = 0.0, 0.0, 0
     np.random.seed(3)
     for it in range(a.warmup + a.steps):
@@ -704,29 +717,10 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
     next_buf = torch.zeros((E, 8), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     status_buf = torch.zeros((E,), dtype=torch.int8).pin_memory().numpy()
     acts_buf = torch.zeros((E,), dtype=torch.int8).pin_memory().numpy()
-    # Staggered synthetic positions spread over ALL game phases, the distribution the device-resident loop measures in
-    # (its envs have been auto-resetting for 150 plies): every env plays one random-move game to its end and starts from a
-    # uniformly random ply of it.  (Until round 2's last bench this was "random moves to a random depth below 50", which
-    # has no late-game positions: 3.6-3.9 k leaves per simulation instead of 3.0-3.3 k, i.e. beyond the 3552 leaves the
-    # trunk evaluates in two passes per SM - a different workload from the one `value` is quoted on.)
-    cur = np.zeros((E, 8), dtype=np.uint32)
-    hist = [cur.copy()]
-    alive = np.ones(E, dtype=bool)
-    length = np.zeros(E, dtype=np.int64)
-    for _ in range(81):
-        idx = np.flatnonzero(alive)
-        if idx.size == 0:
-            break
-        mask = tb.rules_legal_mask(cur[idx]).astype(bool)
-        acts = (rng.random_sample(mask.shape) * mask).argmax(1).astype(np.int8)      # a uniformly random legal move
-        nxt, st = tb.rules_step(cur[idx], acts)
-        cur[idx] = nxt
-        length[idx] += 1
-        alive[idx[st != 0]] = False
-        hist.append(cur.copy())
-    pick = (rng.random_sample(E) * length).astype(np.int64)          # a ply before the game's last move: never terminal
-    states[:] = np.stack(hist)[pick, np.arange(E)]
-    ply_no = pick.copy()
+    # Positions over all game phases (all_phase_positions).  Until round 2's last bench this was "random moves to a random
+    # depth below 50", which has no late-game positions: 3.6-3.9 k leaves per simulation instead of 3.0-3.4 k, i.e. beyond
+    # the 3552 leaves the trunk evaluates in two passes per SM - a different workload from the one `value` is quoted on.
+    states[:], ply_no = all_phase_positions(tb, rng, E)
     eng.reset(-1)
     eng.reset_stats()
     h2d = E * 32 + E * 32 + E          # roots + positions and actions handed to tc_rules_step
