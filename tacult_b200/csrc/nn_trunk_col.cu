@@ -273,11 +273,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     if (marks) marks[1] = clock64();
     griddep_wait();
     if (marks) marks[2] = clock64();
+    // The live positions are dealt out round-robin: CTA b owns rows b, b + grid, b + 2 grid, ...  Which rows those are does
+    // not depend on the leaf count, so the first pass's positions are fetched together WITH the count instead of after it
+    // (one L2 round trip less on the critical path); rows beyond the count are dropped when it arrives.
+    const int grid = (int)gridDim.x;
+    uint32_t first_word = 0u;
+    if (P.states && warp < GMAX && lane < 8 && (int)blockIdx.x + warp * grid < P.batch)
+        first_word = P.states[8 * (size_t)((int)blockIdx.x + warp * grid) + lane];
     int count = P.batch;
     if (P.count_dev) count = min(count, *P.count_dev);
-    const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int p_begin = min(count, (int)blockIdx.x * per), p_end = min(count, p_begin + per);
-    const int n_pass = (p_end - p_begin + GMAX - 1) / GMAX;
+    const int my_n = count > (int)blockIdx.x ? (count - (int)blockIdx.x - 1) / grid + 1 : 0;
+    const int n_pass = (my_n + GMAX - 1) / GMAX;
+    auto row_of = [&](int k) { return (int)blockIdx.x + k * grid; };          // k-th position of this CTA
     if (n_pass == 0 && threadIdx.x == 0) {
         griddep_launch(P.pdl_trigger == 2);
         mbar_wait(wfull, 0u);                   // nothing to do: let the stem weights land before the CTA retires
@@ -290,8 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     // Planes of one position -> channels 0..15 of its 81 rows of the planes buffer, by one warp: the legal mask is
     // computed ONCE, by the warp (rules_warp.cuh), then lane writes cells lane, lane + 32, lane + 64 (per-cell scalar
     // rules made this phase 8.7 k cycles per pass, a fifth of the kernel).
-    auto encode_position = [&](int g, int row) {
-        const uint32_t w = lane < 8 ? P.states[8 * (size_t)row + lane] : 0u;
+    auto encode_position = [&](int g, uint32_t w) {          // w: lane k < 8 holds word k of the packed position
         uint32_t wd[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) wd[k] = __shfl_sync(0xFFFFFFFFu, w, k);
@@ -314,14 +320,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         }
     };
     // dense planes (tc_forward_obs_dev): consecutive threads write consecutive rows of one tile
-    auto encode_dense = [&](int pos0, int G, int tid, int nthreads) {
+    auto encode_dense = [&](int k0, int G, int tid, int nthreads) {       // k0: local index of the pass's first position
         for (int idx = tid; idx < G * 81; idx += nthreads) {
             const int cc = idx / (9 * G), gr = idx - 9 * G * cc;
             const int g = gr / 9, r = gr - 9 * g;
             const int a = 9 * r + cc;
             float v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = c < P.in_planes ? P.obs[((size_t)(pos0 + g) * P.in_planes + c) * 81 + a] : 0.f;
+            for (int c = 0; c < 16; ++c) v[c] = c < P.in_planes ? P.obs[((size_t)row_of(k0 + g) * P.in_planes + c) * 81 + a] : 0.f;
             uint4 o0, o1;
             o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
             o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
@@ -335,11 +341,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
 
     // ---- planes of the first pass: every warp helps ----
     {
-        const int G0 = min(GMAX, p_end - p_begin);
+        const int G0 = min(GMAX, my_n);
         if (P.states) {
-            if (warp < G0) encode_position(warp, p_begin + warp);
+            if (warp < G0) encode_position(warp, first_word);
         } else {
-            encode_dense(p_begin, G0, (int)threadIdx.x, THREADS);
+            encode_dense(0, G0, (int)threadIdx.x, THREADS);
         }
         fence_async_smem();
         __syncthreads();
@@ -412,12 +418,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         //       the planes buffer is free (a barrier of its own: a parity wait cannot skip phases of a shared one) =====
         for (int pass = 1; pass < n_pass; ++pass) {
             mbar_wait(pfree, (uint32_t)(pass - 1) & 1u);
-            const int pos0 = p_begin + pass * GMAX;
-            const int G = min(GMAX, p_end - pos0);
+            const int k0 = pass * GMAX;
+            const int G = min(GMAX, my_n - k0);
             if (P.states) {
-                for (int g = warp - 2; g < G; g += FIRST_EPI - 2) encode_position(g, pos0 + g);
+                for (int g = warp - 2; g < G; g += FIRST_EPI - 2)
+                    encode_position(g, lane < 8 ? P.states[8 * (size_t)row_of(k0 + g) + lane] : 0u);
             } else {
-                encode_dense(pos0, G, (int)threadIdx.x - 64, 32 * (FIRST_EPI - 2));
+                encode_dense(k0, G, (int)threadIdx.x - 64, 32 * (FIRST_EPI - 2));
             }
             fence_async_smem();
             __syncwarp();
@@ -429,9 +436,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         const int i = 32 * quarter + lane;                       // lane of every tile = (position, board row)
         const int g = i / PITCH, r = i - PITCH * g;
         for (int pass = 0; pass < n_pass; ++pass) {
-            const int pos0 = p_begin + pass * GMAX;
-            const int G = min(GMAX, p_end - pos0);
+            const int k0 = pass * GMAX;
+            const int G = min(GMAX, my_n - k0);
             const bool valid = g < G && r < 9;
+            const size_t out_row = (size_t)row_of(k0 + g);
             for (int l = 0; l < n_layers; ++l) {
                 const uint32_t lc = (uint32_t)(pass * n_layers + l);
                 uint8_t *dst = (l & 1) ? Y : X;
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
                             // contiguous bytes, written by nine adjacent lanes.  (The 62 KB a pass writes leave every SM in
                             // the same 2 k cycles; sending them through shared memory and the TMA engine instead - 576-byte
                             // bulk copies - was measured slower, 44.4 vs 45.1 M sims/s.)
-                            if (last) *reinterpret_cast<uint4 *>(P.out + ((size_t)(pos0 + g) * 81 + 9 * j + r) * C + c) = ov;
+                            if (last) *reinterpret_cast<uint4 *>(P.out + (out_row * 81 + 9 * j + r) * C + c) = ov;
                             else *cell = ov;
                         }
                     }
@@ -498,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
-    if (marks) { marks[11] = clock64(); marks[12] = n_pass; marks[13] = p_end - p_begin; }
+    if (marks) { marks[11] = clock64(); marks[12] = n_pass; marks[13] = my_n; }
 }
 
 static size_t smem_bytes() { return 1024 + 2 * (size_t)BUF_BYTES + 2 * (size_t)W_BUF + PBUF_BYTES + (3 * BAR_STRIDE + 6) * 8 + 16; }
