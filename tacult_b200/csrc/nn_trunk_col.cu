@@ -305,12 +305,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_trunk_col(const __grid_constant_
         uint32_t am[3], mm[3], oo[3];
         int status;
         warp_legal_mask<true>(p, lane, am, status, mm, oo);
+        // lane -> cell in COLUMN-major order (consecutive lanes = consecutive board rows of one tile, 32 bytes apart): in
+        // action order consecutive lanes are consecutive tiles, 4 KB apart on the same banks - 26 wavefronts per store
+        // instead of 4-8 (ncu source page), 2.5 k wavefront-cycles per SM and launch stolen from the operand fetch
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const int a = lane + 32 * q;
-            if (a < 81) {
-                const bool mine = (mm[q] >> lane) & 1u, occ = (oo[q] >> lane) & 1u, legal = (am[q] >> lane) & 1u;
-                const int r = (a * 57) >> 9, cc = a - 9 * r;
+            const int idx = lane + 32 * q;
+            if (idx < 81) {
+                const int cc = (idx * 57) >> 9, r = idx - 9 * cc;       // idx / 9, idx % 9
+                const int a = 9 * r + cc, wsel = a >> 5, bit = a & 31;
+                const uint32_t wm = wsel == 0 ? mm[0] : (wsel == 1 ? mm[1] : mm[2]);
+                const uint32_t wo = wsel == 0 ? oo[0] : (wsel == 1 ? oo[1] : oo[2]);
+                const uint32_t wl = wsel == 0 ? am[0] : (wsel == 1 ? am[1] : am[2]);
+                const bool mine = (wm >> bit) & 1u, occ = (wo >> bit) & 1u, legal = (wl >> bit) & 1u;
                 const uint32_t off = (uint32_t)(LEAD + 128 * cc + PITCH * g + r) * 32u;
                 // bf16 1.0 = 0x3F80: planes mine, theirs | legal, ones; channels 4..15 are zero
                 *reinterpret_cast<uint4 *>(Pl + swz32(off)) =
