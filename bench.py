@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--evaluator", default="auto", choices=["auto", "f32", "bf16", "bf16_masked"],
                     help="bf16_masked = production mode (masked soft-max in the heads kernel); not the parity-mode headline")
     ap.add_argument("--stagger-plies", type=int, default=150)
+    ap.add_argument("--settle-plies", type=int, default=0,
+                    help="extra untimed plies at the full simulation count after the stagger (exploration only: the leaf count per "
+                         "step moves in waves as games end and restart, and the trunk's two-pass capacity of 3552 leaves is a cliff - "
+                         "DESIGN.md section 4 lists value for 0 / 6 / 20 / 40 / 80 settling plies)")
     ap.add_argument("--profile-plies", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-envs", type=int, default=64,
@@ -309,6 +313,9 @@ def run_b200(a):
     seed = 1000 + rank
     eng.selfplay_begin(2, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True, discard_records=True)
     eng.selfplay_step(a.stagger_plies)                       # spread the envs over all game phases
+    if a.settle_plies > 0:
+        eng.selfplay_configure(sims, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True, discard_records=True)
+        eng.selfplay_step(a.settle_plies)                    # trees as they are in the steady state (re-used subtrees)
     eng.selfplay_configure(sims, CPUCT, TEMP_THRESHOLD, seed=seed, auto_reset=True)   # records kept from here on
     eng.selfplay_step(a.warmup)
     eng.selfplay_sync()
@@ -394,8 +401,9 @@ def run_b200(a):
             "scaling": "weak", "vs_baseline": None, "dtype": evaluator, "data": "synthetic",
             "config": workload_config(a),
             "measured_region": f"steady state: {a.stagger_plies} plies @2 sims with auto-reset spread the envs over all "
-                               f"game phases, then {a.warmup} warm-up + {a.steps} timed plies with auto-reset; the "
-                               f"reference's own iteration shape is under c3_full_iteration",
+                               f"game phases, then {a.settle_plies} settling + {a.warmup} warm-up + {a.steps} timed plies at "
+                               f"the full simulation count with auto-reset; the reference's own iteration shape (every "
+                               f"transient included) is under c3_full_iteration",
             "leaf_evals_per_sec": leaves * world / (ms * 1e-3),
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
@@ -490,7 +498,8 @@ def run_dropin(a, eng, tb, torch, evaluator):
     states, ply_no = all_phase_positions(tb, rng, E)        # the same distribution as the `e2e` leg
     total_s, pack_s, n_timed = 0.0, 0.0, 0
     np.random.seed(3)
-    for it in range(a.warmup + a.steps):
+    n_untimed = a.settle_plies + a.warmup
+    for it in range(n_untimed + a.steps):
         boards = [GameState.from_packed(s) for s in states]               # the caller's objects
         temps = (ply_no + 1) < TEMP_THRESHOLD
         torch.cuda.synchronize()
@@ -500,7 +509,7 @@ def run_dropin(a, eng, tb, torch, evaluator):
         t1 = time.perf_counter()
         tb.pack_gamestates(boards)
         dp = time.perf_counter() - t1
-        if it >= a.warmup:
+        if it >= n_untimed:
             total_s += dt
             pack_s += dp
             n_timed += 1
@@ -743,7 +752,7 @@ def run_e2e(a, eng, tb, torch, rank, barrier, reduce_scalar, dist, world):
             eng.reset_envs(done)
         return E * sims
 
-    for _ in range(a.warmup):
+    for _ in range(a.settle_plies + a.warmup):            # settle: the same untimed plies as the device-resident loop's
         one_ply()
     k0 = eng.stats()
     barrier()

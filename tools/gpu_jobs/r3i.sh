@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
-python bench.py --skip-cpu-baseline --steps 8 2>gpurun_out/r3i.err | tail -1 > gpurun_out/r3i_bench.json; python -c "
-import json
-d=json.load(open('gpurun_out/r3i_bench.json'))
-print(round(d['value']/1e6,2), d['e2e']['value'], d['e2e_dropin'], d['c3_full_iteration']['value'])"
-tail -3 gpurun_out/r3i.err
+for s in 0 6 20 40 80; do
+python bench.py --skip-cpu-baseline --skip-extras --skip-e2e --settle-plies $s 2>/dev/null | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print($s, round(d['value']/1e6,2), round(d['ms_per_step'],3), d['roofline']['rows_per_launch'], round(d['roofline']['frac'],3))"
+done
