@@ -623,7 +623,13 @@ static int upload_impl(NetBF16Impl &m, const FoldedNet &f, int cap, bool share_s
     // the cells of a position in column-major order
     {
         const char *fz = getenv("TACULT_FUSED"), *cz = getenv("TACULT_TRUNK_COL");
-        m.col = trunk_col_supported(C, I) && !share_sm && (!fz || atoi(fz) != 0) && (!cz || atoi(cz) != 0);
+        // A pass of the column-tiled trunk costs the same for 1 or 12 positions per SM (9 tiles x 7 layers x ~430 cycles); the
+        // tap-per-UMMA trunk costs ~840 cycles per layer and 128 rows (1.28 positions).  Below ~6 positions per SM - engines
+        // of up to 768 rows, e.g. the arena's 512 boards - the older kernel is the faster one (leaf-evaluation sweep at batch
+        // 256: 7.3 vs 6.3 M evals/s; at 1024: 21.2 vs 24.0).  The choice is per engine (its capacity), never per call: a
+        // row's result does not depend on the batch it is evaluated in.  TACULT_TRUNK_COL=2 forces the column trunk.
+        const bool big_enough = cap > 768 || (cz && atoi(cz) == 2);
+        m.col = trunk_col_supported(C, I) && !share_sm && (!fz || atoi(fz) != 0) && (!cz || atoi(cz) != 0) && big_enough;
     }
     // fc1: [E][c*81+p] (NCHW flatten, network.py:92) -> [E][p'*C+c] to match the NHWC activations, p' = p or its transpose
     std::vector<__nv_bfloat16> fb((size_t)E * 81 * C);
