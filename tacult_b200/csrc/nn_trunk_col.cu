@@ -118,14 +118,6 @@ __device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits, 
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <int SWB>
-__device__ __forceinline__ uint64_t desc_of(uint32_t saddr)
-{
-    constexpr uint32_t layout = SWB == 128 ? 2u : (SWB == 64 ? 4u : 6u);
-    constexpr uint32_t hi = ((8u * SWB) >> 4) | (1u << 14) | (layout << 29);
-    return ((uint64_t)hi << 32) | (uint64_t)(saddr >> 4);
-}
-
 // Offsets of the shared-memory carve-up from its 1024-aligned base: compile-time constants, so that every UMMA
 // descriptor of the issue loop is (uniform base + constant) and is built in the uniform datapath.  A descriptor that
 // travels through a vector register costs an R2UR, and those were measured at ~35 cycles each in the issuing thread:
