@@ -56,3 +56,6 @@ def test_every_pass_count_gives_the_same_rows():
         assert np.array_equal(p1, pi[:b]) and np.array_equal(v1, v[:b]), b
     rpi, rv = resnet_oracle.forward(sd, obs_of(states[5220:5476]))
     assert np.abs(pi[5220:] - rpi.numpy()).max() < TOL_BF16 and np.abs(v[5220:] - rv.numpy().ravel()).max() < TOL_BF16
+    # dense observation planes (tc_forward) through all four passes: the same rows as the packed positions
+    pi_d, v_d = eng.forward(obs_of(states[:5476]), BF16)
+    assert np.array_equal(pi_d, pi) and np.array_equal(v_d, v)
